@@ -1,0 +1,30 @@
+# Builds the C-ABI shared library (hand-written sm_100a CUDA) in-tree.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas --expt-relaxed-constexpr
+SRC := ssr_eval_b200/csrc
+OBJ := build/obj
+LIB := ssr_eval_b200/lib/libssr_b200.so
+SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu
+OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(SRCS))
+HDRS := $(SRC)/common.cuh $(SRC)/fft_core.cuh $(SRC)/stft_tables.hpp include/ssr_b200.h
+
+all: $(LIB)
+
+$(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) $(PTXAS_V) -c $< -o $@
+
+$(LIB): $(OBJS)
+	@mkdir -p $(dir $(LIB))
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -cudart static
+
+# host-side emulation harness for the FFT core (no GPU needed)
+build/host_emul: tests/host_emul.cu $(SRC)/fft_core.cuh
+	@mkdir -p build
+	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -o $@ $<
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all clean

@@ -1,0 +1,121 @@
+/*
+ * ssr_b200.h -- C ABI of the B200-native ssr_eval DSP hot path (libssr_b200.so).
+ *
+ * The reference (haoheliu/ssr_eval) is pure Python and has no FFI: its boundary for this path is
+ * a Python class API.  These entry points are what a binding for that path
+ * binds; each cites the reference interface it replaces (paths relative to the reference repo).
+ * Plain pointers and sizes only: no torch / C++ types.  All `*_dev` pointers are CUDA device
+ * pointers owned by the caller; `stream` is a `cudaStream_t` passed as `void*` (NULL = default
+ * stream).  Every call is asynchronous on `stream` unless stated otherwise, allocates no device
+ * memory (workspace is caller-provided; size queries below) and returns an `int` status
+ * (0 = SSR_OK).  Nothing throws across the ABI; `ssr_last_error()` gives the message of the last
+ * failure on the calling thread.
+ *
+ * Ragged batches: utterance i of a batch lives at `x_dev[offsets[i] .. offsets[i+1])` (float32).
+ * Offsets are given twice -- `offsets_host` (used on the host to size grids / workspaces) and
+ * `offsets_dev` (the same n+1 int64 values in device memory, read by the kernels).
+ */
+#ifndef SSR_B200_H_
+#define SSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSR_OK 0
+#define SSR_ERR_INVALID 1   /* bad argument */
+#define SSR_ERR_CUDA 2      /* a CUDA runtime call / launch failed */
+#define SSR_ERR_WORKSPACE 3 /* workspace too small */
+
+/* metric selection flags; out layout is out[pair*4 + {0:lsd, 1:log_sispec, 2:sispec, 3:ssim}] */
+#define SSR_METRIC_LSD 1u
+#define SSR_METRIC_LOG_SISPEC 2u
+#define SSR_METRIC_SISPEC 4u
+#define SSR_METRIC_SSIM 8u
+#define SSR_METRIC_ALL 15u
+
+int ssr_version(void);
+const char* ssr_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench accounting) */
+uint64_t ssr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 + K2: batched STFT -> magnitude -> {LSD, log-sispec, sispec, SSIM}
+ * Replaces AudioMetrics.__init__/wav_to_spectrogram/lsd/sispec/ssim and the metric half of
+ * AudioMetrics.evaluation (ssr_eval/metrics.py:16-19, 26-30, 92-132; ssr_eval/utils.py:43-92).
+ * STFT semantics = librosa.stft(y, n_fft, hop) 0.9.x: centre, reflect pad n_fft//2, periodic Hann
+ * (float64), float64 transform, complex64 store, float32 magnitude.  Any n_fft in [65, 8192]
+ * (power of two: direct FFT; otherwise Bluestein), any hop >= 1.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssr_stft_plan ssr_stft_plan;
+
+/* window_host: n_fft float64 values (the analysis window), or NULL for the periodic Hann.
+ * Synchronous (uploads twiddle / chirp tables to the current device). */
+int ssr_stft_plan_create(ssr_stft_plan** plan, int n_fft, int hop, const double* window_host);
+int ssr_stft_plan_destroy(ssr_stft_plan* plan);
+/* frames of a centred STFT of `length` samples: 1 + (length + 2*(n_fft/2) - n_fft) / hop */
+int64_t ssr_stft_num_frames(const ssr_stft_plan* plan, int64_t length);
+
+/* workspace bytes needed by ssr_stft_metrics_batched for this batch and flag set */
+size_t ssr_stft_metrics_workspace_bytes(const ssr_stft_plan* plan, const int64_t* offsets_host,
+                                        int n_pairs, unsigned flags);
+
+/* est_dev / tgt_dev: the two ragged float32 batches (same offsets: the reference truncates both
+ * waveforms of a pair to the shorter, metrics.py:89-90 -- the caller does that when packing).
+ * Every utterance needs length > n_fft/2 (reflect padding).  out_dev: n_pairs*4 float64;
+ * metrics not requested in `flags` are written as NaN. */
+int ssr_stft_metrics_batched(const ssr_stft_plan* plan, const float* est_dev, const float* tgt_dev,
+                             const int64_t* offsets_host, const int64_t* offsets_dev, int n_pairs,
+                             unsigned flags, double* out_dev, void* workspace_dev,
+                             size_t workspace_bytes, void* stream);
+
+/* Magnitude spectrogram only (AudioMetrics.wav_to_spectrogram, metrics.py:26-30) of one ragged
+ * batch: spec_dev receives, utterance after utterance, T_i x F float32 row-major (F = n_fft/2+1).
+ * Needs the same workspace as ssr_stft_metrics_batched with flags = 0. */
+int ssr_stft_magnitude_batched(const ssr_stft_plan* plan, const float* x_dev,
+                               const int64_t* offsets_host, const int64_t* offsets_dev, int n,
+                               float* spec_dev, void* workspace_dev, size_t workspace_bytes,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3: polyphase FIR resampler = scipy.signal.resample_poly(x, up, down) (upfirdn, zero
+ * extension) for a given FIR.  Replaces the resample_poly calls of subsampling()
+ * (ssr_eval/lowpass.py:134-144) and of librosa.resample(res_type="polyphase")
+ * (ssr_eval/eval.py:144-150).  `taps_host` is scipy's `h` AFTER the `h *= up` scaling and BEFORE
+ * its zero padding: n_taps = 2*half_len+1 float32 values (firwin(..., ("kaiser", 5.0))).
+ * up/down must already be gcd-reduced.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssr_resample_plan ssr_resample_plan;
+int ssr_resample_plan_create(ssr_resample_plan** plan, int up, int down, const float* taps_host,
+                             int n_taps);
+int ssr_resample_plan_destroy(ssr_resample_plan* plan);
+/* ceil(n_in * up / down) */
+int64_t ssr_resample_out_len(const ssr_resample_plan* plan, int64_t n_in);
+int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
+                              const int64_t* in_offsets_host, const int64_t* in_offsets_dev,
+                              float* y_dev, const int64_t* out_offsets_host,
+                              const int64_t* out_offsets_dev, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4: STFT hard low-pass = stft_hard_lowpass_v0 (ssr_eval/lowpass.py:17-28) through
+ * FDomainHelper.wav_to_spectrogram_phase / spectrogram_phase_to_wav (ssr_eval/dsp.py:76-119):
+ * STFT (n_fft, hop, periodic Hann, centre, reflect) -> mag/cos/sin with eps 1e-8 -> zero bins
+ * >= cut_bin -> ISTFT (x window / n_fft, overlap-add, / clamp(overlap-added window^2, 1e-11))
+ * -> drop n_fft/2 -> exactly `length` samples.  float32 arithmetic.  n_fft must be a power of
+ * two in [256, 4096]; the reference always uses n_fft 2048 / hop 441 (dsp.py:9-10).
+ * cut_bins_dev: one int32 per utterance = int((n_fft/2+1) * lowpass_ratio).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssr_lowpass_plan ssr_lowpass_plan;
+int ssr_lowpass_plan_create(ssr_lowpass_plan** plan, int n_fft, int hop);
+int ssr_lowpass_plan_destroy(ssr_lowpass_plan* plan);
+int ssr_stft_hard_lowpass_batched(const ssr_lowpass_plan* plan, const float* x_dev,
+                                  const int64_t* offsets_host, const int64_t* offsets_dev, int n,
+                                  const int32_t* cut_bins_dev, float* y_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSR_B200_H_ */

@@ -1,0 +1,45 @@
+"""CPU oracle for the ssr_eval DSP hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import anything from this package, and only as the
+checker (or as the reported CPU baseline), never as the thing shipped.  The product
+package ``ssr_eval_b200`` never imports ``oracle`` and has no CPU fallback.
+
+What this is
+------------
+A CPU restatement (numpy + scipy + torch, the same upstream numerics the reference
+delegates to) of the algorithm of haoheliu/ssr_eval's metric / degradation path:
+
+* in-repo formulas are restated from the reference source, each function citing the
+  ``file:line`` it follows (paths relative to ``/root/reference``);
+* third-party semantics whose packages are absent from this image
+  (``librosa`` 0.9.x, ``scikit-image`` 0.19.x, ``torchlibrosa`` 0.0.7-0.0.9) are
+  restated from their published behaviour; ``scipy.signal.resample_poly``,
+  ``scipy.ndimage.uniform_filter``, ``numpy.fft`` and every ``torch`` op are the SAME
+  upstream code the reference calls and are called directly.
+
+Pinning status (see DESIGN.md, section "Oracle")
+-----------------------------------------------
+* In-repo arithmetic (lsd / sispec / to_log / energy_unify / truncation / zero-bin rule /
+  subsampling ratios / lowpass dispatch / aggregation): PINNED -- the golden fixtures under
+  ``tests/golden/`` were produced by importing and running the reference's own
+  ``ssr_eval.metrics.AudioMetrics`` / ``ssr_eval.lowpass.lowpass`` /
+  ``ssr_eval.utils.dict_mean`` code from ``/root/reference`` (script:
+  ``tests/golden/make_golden.py``) with the missing third-party packages replaced by the
+  shims in ``oracle/shims`` (which are built from this restatement).
+* ``scipy.signal.resample_poly``: PINNED by the installed scipy (called directly).
+* ``librosa.stft`` framing / ``skimage...structural_similarity`` / ``torchlibrosa``
+  STFT+ISTFT / ``librosa.resample`` wrapper: PARITY UNPINNED by any test or fixture of the
+  reference (it has none); restated from the documented behaviour of the
+  era-consistent versions and cross-checked against independent implementations
+  (``torch.stft`` in float64, brute-force SSIM, ``numpy.fft.irfft`` overlap-add).
+"""
+from .stft import hann_periodic, stft_complex, stft_mag, n_frames  # noqa: F401
+from .metrics import (  # noqa: F401
+    EPS, AudioMetricsOracle, lsd, sispec, to_log, energy_unify, pow_norm, pow_p_norm,
+    ssim_skimage, evaluation, dict_mean,
+)
+from .lowpass import (  # noqa: F401
+    TorchlibrosaSTFT, TorchlibrosaISTFT, FDomainHelperOracle, stft_hard_lowpass_v0,
+    subsampling, align_length, lowpass, librosa_resample_polyphase, resample_poly,
+)

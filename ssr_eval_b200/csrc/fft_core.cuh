@@ -1,0 +1,205 @@
+// fft_core.cuh -- in-place shared-memory FFT building blocks (float / double), host+device.
+//
+// Forward transform  : decimation-in-frequency passes, natural order in -> digit-reversed out.
+// Inverse transform  : decimation-in-time passes,  digit-reversed in  -> natural order out
+//                      (unnormalised; the exact conjugate-transpose of the forward passes).
+// Radices 8 and 4 only: M = 2^m = 8^a * 4^b.  A pass touches, per butterfly, the same R
+// locations for read and write, so one buffer suffices (no Stockham ping-pong) and the only
+// synchronisation is one barrier between passes.
+//
+// Bank conflicts: element i lives at pad(i) = i + (i >> 3).  With 16-byte (double2) or 8-byte
+// (float2) elements this makes the stride-8 / stride-4 accesses of the last passes and the
+// unit-stride accesses of the first passes conflict-free per quarter/half warp.
+//
+// Everything is SSR_HD so that tests/host_emul.cu can run the very same code on the CPU
+// (threads emulated by a loop) -- the container that builds this has no GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SSR_HD __host__ __device__ __forceinline__
+#else
+#define SSR_HD inline
+#endif
+
+namespace ssr {
+
+template <typename T>
+struct alignas(2 * sizeof(T)) C2 {
+  T x, y;
+};
+using cd = C2<double>;
+using cf = C2<float>;
+
+template <typename T>
+SSR_HD C2<T> cmul(C2<T> a, C2<T> b) {
+  return C2<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T>
+SSR_HD C2<T> cmul_conj(C2<T> a, C2<T> b) {  // a * conj(b)
+  return C2<T>{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y};
+}
+template <typename T>
+SSR_HD C2<T> cadd(C2<T> a, C2<T> b) {
+  return C2<T>{a.x + b.x, a.y + b.y};
+}
+template <typename T>
+SSR_HD C2<T> csub(C2<T> a, C2<T> b) {
+  return C2<T>{a.x - b.x, a.y - b.y};
+}
+// multiply by -i (forward) or +i (inverse)
+template <bool INV, typename T>
+SSR_HD C2<T> mul_mi(C2<T> v) {
+  return INV ? C2<T>{-v.y, v.x} : C2<T>{v.y, -v.x};
+}
+
+SSR_HD int pad_idx(int i) { return i + (i >> 3); }
+SSR_HD int padded_size(int M) { return M + (M >> 3); }
+
+// y_q = sum_r x_r W4^{rq}, W4 = exp(-+ 2 pi i / 4)
+template <bool INV, typename T>
+SSR_HD void bfly4(C2<T>& x0, C2<T>& x1, C2<T>& x2, C2<T>& x3) {
+  C2<T> a0 = cadd(x0, x2), a1 = csub(x0, x2), a2 = cadd(x1, x3), a3 = csub(x1, x3);
+  C2<T> a3r = mul_mi<INV>(a3);
+  x0 = cadd(a0, a2);
+  x2 = csub(a0, a2);
+  x1 = cadd(a1, a3r);
+  x3 = csub(a1, a3r);
+}
+
+template <bool INV, typename T>
+SSR_HD void bfly8(C2<T>* x) {
+  // even / odd radix-4 sub-transforms
+  C2<T> e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6];
+  C2<T> o0 = x[1], o1 = x[3], o2 = x[5], o3 = x[7];
+  bfly4<INV>(e0, e1, e2, e3);
+  bfly4<INV>(o0, o1, o2, o3);
+  const T h = (T)0.70710678118654752440;
+  // W8^1 = (1 -+ i)/sqrt2, W8^2 = -+i, W8^3 = (-1 -+ i)/sqrt2
+  C2<T> t1 = INV ? C2<T>{(o1.x - o1.y) * h, (o1.x + o1.y) * h}
+                 : C2<T>{(o1.x + o1.y) * h, (o1.y - o1.x) * h};
+  C2<T> t2 = mul_mi<INV>(o2);
+  C2<T> t3 = INV ? C2<T>{(-o3.x - o3.y) * h, (o3.x - o3.y) * h}
+                 : C2<T>{(o3.y - o3.x) * h, (-o3.x - o3.y) * h};
+  x[0] = cadd(e0, o0);
+  x[4] = csub(e0, o0);
+  x[1] = cadd(e1, t1);
+  x[5] = csub(e1, t1);
+  x[2] = cadd(e2, t2);
+  x[6] = csub(e2, t2);
+  x[3] = cadd(e3, t3);
+  x[7] = csub(e3, t3);
+}
+
+template <int R, bool INV, typename T>
+SSR_HD void bfly(C2<T>* x) {
+  if (R == 8) {
+    bfly8<INV>(x);
+  } else {
+    bfly4<INV>(x[0], x[1], x[2], x[3]);
+  }
+}
+
+// number of radix-8 / radix-4 passes for M = 2^logM
+SSR_HD constexpr int n_r4(int logM) { return (logM % 3 == 0) ? 0 : ((logM % 3 == 2) ? 1 : 2); }
+SSR_HD constexpr int n_r8(int logM) { return (logM - 2 * n_r4(logM)) / 3; }
+
+// digit-reversed position of frequency k after the forward DIF passes
+inline int dif_position(int k, int logM) {
+  int M = 1 << logM, pos = 0, N = M;
+  int a = n_r8(logM), b = n_r4(logM);
+  for (int s = 0; s < a + b; ++s) {
+    int R = (s < a) ? 8 : 4;
+    pos += (k % R) * (N / R);
+    k /= R;
+    N /= R;
+  }
+  return pos;
+}
+
+// One forward DIF radix-R pass over the whole M-point buffer (sub-transform length Ncur).
+// tw = exp(-2 pi i n / M), n in [0, M).
+template <int R, typename T>
+SSR_HD void dif_pass(C2<T>* buf, int M, int Ncur, const C2<T>* __restrict__ tw, int tid,
+                     int nthreads) {
+  const int sub = Ncur / R;
+  const int tws = M / Ncur;
+  for (int i = tid; i < M / R; i += nthreads) {
+    const int j = i & (sub - 1);
+    const int base = (i - j) * R + j;  // (i / sub) * Ncur + j
+    C2<T> x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) x[r] = buf[pad_idx(base + r * sub)];
+    bfly<R, false>(x);
+    if (sub > 1) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) x[q] = cmul(x[q], tw[j * q * tws]);
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) buf[pad_idx(base + q * sub)] = x[q];
+  }
+}
+
+// One inverse DIT radix-R pass (conjugate twiddles first, then the conjugate butterfly).
+template <int R, typename T>
+SSR_HD void dit_pass(C2<T>* buf, int M, int Ncur, const C2<T>* __restrict__ tw, int tid,
+                     int nthreads) {
+  const int sub = Ncur / R;
+  const int tws = M / Ncur;
+  for (int i = tid; i < M / R; i += nthreads) {
+    const int j = i & (sub - 1);
+    const int base = (i - j) * R + j;
+    C2<T> x[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) x[q] = buf[pad_idx(base + q * sub)];
+    if (sub > 1) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) x[q] = cmul_conj(x[q], tw[j * q * tws]);
+    }
+    bfly<R, true>(x);
+#pragma unroll
+    for (int r = 0; r < R; ++r) buf[pad_idx(base + r * sub)] = x[r];
+  }
+}
+
+// Whole transforms; SYNC is a functor called between passes (and NOT after the last one).
+template <int LOGM, typename T, typename SYNC>
+SSR_HD void fft_forward_dif(C2<T>* buf, const C2<T>* __restrict__ tw, int tid, int nthreads,
+                            SYNC sync) {
+  constexpr int M = 1 << LOGM;
+  constexpr int A = n_r8(LOGM), B = n_r4(LOGM);
+  int N = M;
+#pragma unroll
+  for (int s = 0; s < A + B; ++s) {
+    if (s) sync();
+    if (s < A) {
+      dif_pass<8>(buf, M, N, tw, tid, nthreads);
+      N /= 8;
+    } else {
+      dif_pass<4>(buf, M, N, tw, tid, nthreads);
+      N /= 4;
+    }
+  }
+}
+
+template <int LOGM, typename T, typename SYNC>
+SSR_HD void fft_inverse_dit(C2<T>* buf, const C2<T>* __restrict__ tw, int tid, int nthreads,
+                            SYNC sync) {
+  constexpr int M = 1 << LOGM;
+  constexpr int A = n_r8(LOGM), B = n_r4(LOGM);
+  // reverse pass order: the radix-4 passes (smallest sub-transforms) first
+  int N = 1;
+#pragma unroll
+  for (int s = A + B - 1; s >= 0; --s) {
+    if (s != A + B - 1) sync();
+    if (s < A) {
+      N *= 8;
+      dit_pass<8>(buf, M, N, tw, tid, nthreads);
+    } else {
+      N *= 4;
+      dit_pass<4>(buf, M, N, tw, tid, nthreads);
+    }
+  }
+}
+
+}  // namespace ssr

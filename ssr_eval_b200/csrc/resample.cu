@@ -1,0 +1,131 @@
+// resample.cu -- K3: batched polyphase FIR resampler with scipy.signal.resample_poly semantics.
+//
+// Replaces (paths relative to the reference repo):
+//   ssr_eval/lowpass.py:137,140  resample_poly(data, fs_down, fs_ori) / (y, fs_ori, fs_down)
+//   ssr_eval/eval.py:144-150     librosa.resample(..., res_type="polyphase") -> resample_poly
+// scipy (scipy/signal/_signaltools.py resample_poly + _upfirdn_apply.pyx) does, for float32 x:
+//   n_out = ceil(n_in*up/down); half_len = (len(h)-1)/2; n_pre_pad = down - half_len % down;
+//   n_pre_remove = (half_len + n_pre_pad) / down; h padded with n_pre_pad zeros in front;
+//   y = upfirdn(h_padded, x, up, down)[n_pre_remove : n_pre_remove + n_out]   (zero extension)
+// i.e.  y[j] = sum_i x[i] * h[(j + n_pre_remove)*down - n_pre_pad - i*up], accumulated in float32
+// in ascending i with a separate multiply and add -- reproduced here term for term.
+#include <vector>
+
+#include "common.cuh"
+
+struct ssr_resample_plan {
+  int up, down, n_taps, half_len, n_pre_pad, n_pre_remove, K, device;
+  float* bank;  // [up][K]: bank[phase*K + k] = h[phase + k*up] (0 beyond n_taps)
+};
+
+namespace ssr {
+
+__global__ void __launch_bounds__(256)
+k_resample(const float* __restrict__ x, const long long* __restrict__ in_off, float* __restrict__ y,
+           const long long* __restrict__ out_off, int u0, int up, int down, int n_pre_pad,
+           int n_pre_remove, int K, const float* __restrict__ bank) {
+  const int u = u0 + blockIdx.y;
+  const long long n_out = out_off[u + 1] - out_off[u];
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_out) return;
+  const long long n_in = in_off[u + 1] - in_off[u];
+  const float* xu = x + in_off[u];
+  const long long c = (j + n_pre_remove) * (long long)down - n_pre_pad;
+  long long i_hi = c / up;
+  long long phase = c - i_hi * up;
+  if (phase < 0) {  // floor division for negative c
+    phase += up;
+    i_hi -= 1;
+  }
+  const float* hb = bank + phase * K;
+  float acc = 0.f;
+  for (int k = K - 1; k >= 0; --k) {
+    long long i = i_hi - k;
+    if (i >= 0 && i < n_in) acc = __fadd_rn(acc, __fmul_rn(__ldg(xu + i), __ldg(hb + k)));
+  }
+  y[out_off[u] + j] = acc;
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+extern "C" {
+
+int ssr_resample_plan_create(ssr_resample_plan** out, int up, int down, const float* taps_host,
+                             int n_taps) {
+  if (!out) return fail(SSR_ERR_INVALID, "plan pointer is NULL");
+  *out = nullptr;
+  if (up < 1 || down < 1 || !taps_host || n_taps < 1 || (n_taps % 2) == 0)
+    return fail(SSR_ERR_INVALID, "resample plan: up, down >= 1 and an odd number of taps required");
+  ssr_resample_plan* p = new ssr_resample_plan();
+  p->up = up;
+  p->down = down;
+  p->n_taps = n_taps;
+  p->half_len = (n_taps - 1) / 2;
+  p->n_pre_pad = down - p->half_len % down;
+  p->n_pre_remove = (p->half_len + p->n_pre_pad) / down;
+  p->K = (n_taps + up - 1) / up;
+  std::vector<float> bank((size_t)up * p->K, 0.f);
+  for (int ph = 0; ph < up; ++ph)
+    for (int k = 0; k < p->K; ++k) {
+      long long q = ph + (long long)k * up;
+      if (q < n_taps) bank[(size_t)ph * p->K + k] = taps_host[q];
+    }
+  p->bank = nullptr;
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaMalloc(&p->bank, bank.size() * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(p->bank, bank.data(), bank.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (p->bank) cudaFree(p->bank);
+    delete p;
+    return fail(SSR_ERR_CUDA, std::string("resample plan upload: ") + cudaGetErrorString(e));
+  }
+  *out = p;
+  return SSR_OK;
+}
+
+int ssr_resample_plan_destroy(ssr_resample_plan* plan) {
+  if (!plan) return SSR_OK;
+  if (plan->bank) cudaFree(plan->bank);
+  delete plan;
+  return SSR_OK;
+}
+
+int64_t ssr_resample_out_len(const ssr_resample_plan* plan, int64_t n_in) {
+  if (!plan) return -1;
+  long long t = (long long)n_in * plan->up;
+  return (int64_t)(t / plan->down + (t % plan->down ? 1 : 0));
+}
+
+int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
+                              const int64_t* in_offsets_host, const int64_t* in_offsets_dev,
+                              float* y_dev, const int64_t* out_offsets_host,
+                              const int64_t* out_offsets_dev, int n, void* stream) {
+  if (!plan || !x_dev || !y_dev || !in_offsets_host || !in_offsets_dev || !out_offsets_host ||
+      !out_offsets_dev || n < 1)
+    return fail(SSR_ERR_INVALID, "ssr_resample_poly_batched: bad argument");
+  long long max_out = 0;
+  for (int u = 0; u < n; ++u) {
+    long long n_in = in_offsets_host[u + 1] - in_offsets_host[u];
+    long long n_out = out_offsets_host[u + 1] - out_offsets_host[u];
+    if (n_out != ssr_resample_out_len(plan, n_in))
+      return fail(SSR_ERR_INVALID, "output offsets do not match ceil(n_in*up/down)");
+    if (n_out > max_out) max_out = n_out;
+  }
+  if (max_out == 0) return SSR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int u0 = 0; u0 < n; u0 += 32768) {
+    int nu = n - u0 < 32768 ? n - u0 : 32768;
+    dim3 grid((unsigned)((max_out + 255) / 256), nu);
+    k_resample<<<grid, 256, 0, st>>>(x_dev, reinterpret_cast<const long long*>(in_offsets_dev), y_dev,
+                                     reinterpret_cast<const long long*>(out_offsets_dev), u0, plan->up,
+                                     plan->down, plan->n_pre_pad, plan->n_pre_remove, plan->K,
+                                     plan->bank);
+    SSR_LAUNCH_CHECK("k_resample");
+  }
+  return SSR_OK;
+}
+
+}  // extern "C"

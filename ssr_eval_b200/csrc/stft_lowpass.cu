@@ -1,0 +1,270 @@
+// stft_lowpass.cu -- K4: STFT hard low-pass (STFT -> zero bins >= cut -> ISTFT), float32.
+//
+// Replaces (paths relative to the reference repo):
+//   ssr_eval/lowpass.py:17-28   stft_hard_lowpass_v0
+//   ssr_eval/dsp.py:76-81       spectrogram_phase: mag = clamp(re^2+im^2, eps)^0.5, cos, sin
+//   ssr_eval/dsp.py:83-105      wav_to_spectrogram_phase (eps = 1e-8)
+//   ssr_eval/dsp.py:107-119     spectrogram_phase_to_wav -> torchlibrosa ISTFT
+// torchlibrosa computes the STFT/ISTFT as dense conv1d DFTs in float32; here each CTA runs a
+// shared-memory float32 FFT instead, two real frames packed per complex transform:
+//   z = w*x_f + i*w*x_{f+1} -> FFT -> split -> mag/cos/sin round trip, zero k >= cut
+//   -> Y = X'_f + i*X'_{f+1} (Hermitian extended) -> inverse FFT -> Re = frame f, Im = frame f+1
+//   -> x window / n_fft -> overlap-add in shared memory -> / clamp(sum window^2, 1e-11) -> trim.
+// A work item owns `chunk_hops` hops of output samples and recomputes the <= n_fft/hop halo frames.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "fft_core.cuh"
+
+struct ssr_lowpass_plan {
+  int n_fft, hop, logM, device;
+  void* blob;
+  const ssr::cf* tw;         // exp(-2 pi i n / N), float
+  const float* win;          // float32(hann_periodic[n])
+  const float* win_over_n;   // float32(hann[n] / N)
+  const float* win_sq;       // float32(hann[n]^2)
+  const uint16_t* ppos;      // padded slot of frequency k after the DIF passes
+};
+
+namespace ssr {
+
+constexpr int kLpThreads = 256;
+
+struct LpDev {
+  int N, hop;
+  const cf* tw;
+  const float* win;
+  const float* win_over_n;
+  const float* win_sq;
+  const uint16_t* ppos;
+};
+
+__device__ __forceinline__ long long lp_reflect(long long i, long long L) {
+  if (i >= 0 && i < L) return i;
+  if (L == 1) return 0;
+  long long period = 2 * (L - 1);
+  i %= period;
+  if (i < 0) i += period;
+  return i < L ? i : period - i;
+}
+
+struct LpSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// mag/cos/sin round trip of one bin (dsp.py:76-81 with eps 1e-8, lowpass.py:24-25 zeroing)
+__device__ __forceinline__ cf phase_roundtrip(float re, float im, bool keep) {
+  float mag = sqrtf(fmaxf(re * re + im * im, 1e-8f));
+  float c = re / mag, s = im / mag;
+  if (!keep) mag = 0.f;
+  return cf{mag * c, mag * s};
+}
+
+template <int LOGM>
+__global__ void __launch_bounds__(kLpThreads)
+k_stft_hard_lowpass(LpDev P, const float* __restrict__ x, const long long* __restrict__ offsets,
+                    const int* __restrict__ cut_bins, float* __restrict__ y, int u0, int chunk_hops) {
+  constexpr int N = 1 << LOGM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* buf = reinterpret_cast<cf*>(smem_raw);
+  float* acc = reinterpret_cast<float*>(smem_raw + sizeof(cf) * padded_size(N));
+
+  const int tid = threadIdx.x;
+  const int u = u0 + blockIdx.y;
+  const long long off = offsets[u];
+  const long long L = offsets[u + 1] - off;
+  const int hop = P.hop;
+  const long long n0 = (long long)blockIdx.x * chunk_hops * hop;  // first output sample of this item
+  if (n0 >= L) return;
+  const long long n1 = min(L, n0 + (long long)chunk_hops * hop);
+  const long long m0 = n0 + N / 2, m1 = n1 + N / 2;  // overlap-add coordinates
+  const int span = (int)(m1 - m0);
+  const long long T = L / hop + 1;  // frames of the centred STFT (L + 2*(N/2) - N) / hop + 1
+  const long long f_lo = (m0 - N >= 0) ? (m0 - N) / hop + 1 : 0;
+  const long long f_hi = min(T - 1, (m1 - 1) / hop);
+  const int cut = cut_bins[u];
+  const float* xu = x + off;
+
+  for (int i = tid; i < span; i += kLpThreads) acc[i] = 0.f;
+  __syncthreads();
+
+  for (long long f = f_lo; f <= f_hi; f += 2) {
+    const bool two = (f + 1) <= f_hi;
+    const long long s0 = f * hop - N / 2, s1 = s0 + hop;
+    for (int n = tid; n < N; n += kLpThreads) {
+      float w = P.win[n];
+      float a = w * __ldg(xu + lp_reflect(s0 + n, L));
+      float b = two ? w * __ldg(xu + lp_reflect(s1 + n, L)) : 0.f;
+      buf[pad_idx(n)] = cf{a, b};
+    }
+    __syncthreads();
+    fft_forward_dif<LOGM>(buf, P.tw, tid, kLpThreads, LpSync());
+    __syncthreads();
+    for (int k = tid; k <= N / 2; k += kLpThreads) {
+      const int pa = P.ppos[k], pb = P.ppos[(N - k) & (N - 1)];
+      cf a = buf[pa], b = buf[pb];
+      // X_f = (Z[k] + conj Z[N-k]) / 2 ; X_{f+1} = (Z[k] - conj Z[N-k]) / (2i)
+      float x1r = 0.5f * (a.x + b.x), x1i = 0.5f * (a.y - b.y);
+      float x2r = 0.5f * (a.y + b.y), x2i = 0.5f * (b.x - a.x);
+      const bool keep = k < cut;
+      cf A = phase_roundtrip(x1r, x1i, keep);
+      cf B = phase_roundtrip(x2r, x2i, keep);
+      if (k == 0 || k == N / 2) {  // the imaginary parts of DC / Nyquist never reach the real IDFT
+        A.y = 0.f;
+        B.y = 0.f;
+      }
+      buf[pa] = cf{A.x - B.y, A.y + B.x};                      // Y[k]   = A + iB
+      if (pb != pa) buf[pb] = cf{A.x + B.y, B.x - A.y};        // Y[N-k] = conj(A) + i conj(B)
+    }
+    __syncthreads();
+    fft_inverse_dit<LOGM>(buf, P.tw, tid, kLpThreads, LpSync());
+    __syncthreads();
+    // overlap-add: frame f from the real part, then frame f+1 from the imaginary part
+    for (int n = tid; n < N; n += kLpThreads) {
+      long long m = f * hop + n;
+      if (m >= m0 && m < m1) acc[m - m0] += P.win_over_n[n] * buf[pad_idx(n)].x;
+    }
+    __syncthreads();
+    if (two) {
+      for (int n = tid; n < N; n += kLpThreads) {
+        long long m = (f + 1) * hop + n;
+        if (m >= m0 && m < m1) acc[m - m0] += P.win_over_n[n] * buf[pad_idx(n)].y;
+      }
+    }
+    __syncthreads();
+  }
+
+  for (int i = tid; i < span; i += kLpThreads) {
+    const long long m = m0 + i;
+    long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
+    long long fb = min(T - 1, m / hop);
+    float ws = 0.f;
+    for (long long f = fa; f <= fb; ++f) ws += P.win_sq[m - f * hop];
+    ws = fmaxf(ws, 1e-11f);
+    y[off + (m - N / 2)] = acc[i] / ws;
+  }
+}
+
+static int lp_chunk_hops(int hop) {
+  int c = 14336 / hop;  // accumulator <= 56 KB
+  if (c > 32) c = 32;
+  if (c < 1) c = 1;
+  return c;
+}
+
+template <int LOGM>
+static int launch_lp(const ssr_lowpass_plan* plan, const float* x, const long long* offs,
+                     const int* cut, float* y, int n, long long max_len, cudaStream_t st) {
+  LpDev P{plan->n_fft, plan->hop, plan->tw, plan->win, plan->win_over_n, plan->win_sq, plan->ppos};
+  const int ch = lp_chunk_hops(plan->hop);
+  size_t smem = sizeof(cf) * (size_t)padded_size(plan->n_fft) + sizeof(float) * (size_t)ch * plan->hop;
+  auto kern = k_stft_hard_lowpass<LOGM>;
+  SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long per = (long long)ch * plan->hop;
+  unsigned gx = (unsigned)((max_len + per - 1) / per);
+  for (int u0 = 0; u0 < n; u0 += 32768) {
+    int nu = n - u0 < 32768 ? n - u0 : 32768;
+    kern<<<dim3(gx, nu), kLpThreads, smem, st>>>(P, x, offs, cut, y, u0, ch);
+    SSR_LAUNCH_CHECK("k_stft_hard_lowpass");
+  }
+  return SSR_OK;
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+extern "C" {
+
+int ssr_lowpass_plan_create(ssr_lowpass_plan** out, int n_fft, int hop) {
+  if (!out) return fail(SSR_ERR_INVALID, "plan pointer is NULL");
+  *out = nullptr;
+  int logM = 0;
+  while ((1 << logM) < n_fft) ++logM;
+  if ((1 << logM) != n_fft || logM < 8 || logM > 12)
+    return fail(SSR_ERR_INVALID, "stft_hard low-pass needs a power-of-two n_fft in [256, 4096]");
+  if (hop < 1 || hop > n_fft) return fail(SSR_ERR_INVALID, "hop must be in [1, n_fft]");
+  const long double PI = 3.14159265358979323846264338327950288L;
+  const int N = n_fft;
+  size_t o = 0;
+  size_t o_tw = o;
+  o = align_up(o + sizeof(cf) * (size_t)N, 256);
+  size_t o_w = o;
+  o = align_up(o + sizeof(float) * (size_t)N, 256);
+  size_t o_wn = o;
+  o = align_up(o + sizeof(float) * (size_t)N, 256);
+  size_t o_w2 = o;
+  o = align_up(o + sizeof(float) * (size_t)N, 256);
+  size_t o_pos = o;
+  o = align_up(o + sizeof(uint16_t) * (size_t)N, 256);
+  std::vector<unsigned char> host(o, 0);
+  cf* tw = reinterpret_cast<cf*>(host.data() + o_tw);
+  float* w = reinterpret_cast<float*>(host.data() + o_w);
+  float* wn = reinterpret_cast<float*>(host.data() + o_wn);
+  float* w2 = reinterpret_cast<float*>(host.data() + o_w2);
+  uint16_t* ppos = reinterpret_cast<uint16_t*>(host.data() + o_pos);
+  for (int n = 0; n < N; ++n) {
+    long double a = -2 * PI * (long double)n / (long double)N;
+    tw[n] = cf{(float)cosl(a), (float)sinl(a)};
+    double h = (double)(0.5L - 0.5L * cosl(2 * PI * (long double)n / (long double)N));
+    w[n] = (float)h;
+    wn[n] = (float)(h / (double)N);
+    w2[n] = (float)(h * h);
+    ppos[n] = (uint16_t)pad_idx(dif_position(n, logM));
+  }
+  ssr_lowpass_plan* p = new ssr_lowpass_plan();
+  p->n_fft = N;
+  p->hop = hop;
+  p->logM = logM;
+  p->blob = nullptr;
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaMalloc(&p->blob, o);
+  if (e == cudaSuccess) e = cudaMemcpy(p->blob, host.data(), o, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (p->blob) cudaFree(p->blob);
+    delete p;
+    return fail(SSR_ERR_CUDA, std::string("lowpass plan upload: ") + cudaGetErrorString(e));
+  }
+  unsigned char* d = static_cast<unsigned char*>(p->blob);
+  p->tw = reinterpret_cast<const cf*>(d + o_tw);
+  p->win = reinterpret_cast<const float*>(d + o_w);
+  p->win_over_n = reinterpret_cast<const float*>(d + o_wn);
+  p->win_sq = reinterpret_cast<const float*>(d + o_w2);
+  p->ppos = reinterpret_cast<const uint16_t*>(d + o_pos);
+  *out = p;
+  return SSR_OK;
+}
+
+int ssr_lowpass_plan_destroy(ssr_lowpass_plan* plan) {
+  if (!plan) return SSR_OK;
+  if (plan->blob) cudaFree(plan->blob);
+  delete plan;
+  return SSR_OK;
+}
+
+int ssr_stft_hard_lowpass_batched(const ssr_lowpass_plan* plan, const float* x_dev,
+                                  const int64_t* offsets_host, const int64_t* offsets_dev, int n,
+                                  const int32_t* cut_bins_dev, float* y_dev, void* stream) {
+  if (!plan || !x_dev || !offsets_host || !offsets_dev || !cut_bins_dev || !y_dev || n < 1)
+    return fail(SSR_ERR_INVALID, "ssr_stft_hard_lowpass_batched: bad argument");
+  long long max_len = 0;
+  for (int u = 0; u < n; ++u) {
+    long long L = offsets_host[u + 1] - offsets_host[u];
+    if (L < 1) return fail(SSR_ERR_INVALID, "empty utterance in batch");
+    if (L > max_len) max_len = L;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long* offs = reinterpret_cast<const long long*>(offsets_dev);
+  switch (plan->logM) {
+    case 8: return launch_lp<8>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
+    case 9: return launch_lp<9>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
+    case 10: return launch_lp<10>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
+    case 11: return launch_lp<11>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
+    case 12: return launch_lp<12>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
+    default: return fail(SSR_ERR_INVALID, "unsupported n_fft");
+  }
+}
+
+}  // extern "C"

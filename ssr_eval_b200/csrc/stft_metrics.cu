@@ -1,0 +1,685 @@
+// stft_metrics.cu -- K1 (batched STFT -> magnitude -> LSD / sispec / log-sispec accumulators)
+// and K2 (7x7 box-window SSIM) of the ssr_eval hot path, plus their C ABI.
+//
+// Reference semantics (paths relative to the reference repo):
+//   ssr_eval/metrics.py:16-19   n_fft / hop from the sample rate
+//   ssr_eval/metrics.py:26-30   |librosa.stft| : reflect pad, periodic Hann (f64), f64 FFT, c64
+//   ssr_eval/metrics.py:109-112 lsd
+//   ssr_eval/metrics.py:114-121 + ssr_eval/utils.py:68-92   sispec (energy_unify, pow_norm, ...)
+//   ssr_eval/utils.py:43-44     to_log
+//   ssr_eval/metrics.py:123-132 ssim -> skimage structural_similarity(win_size=7)
+//
+// Numerics: est and target of a pair are packed as ONE complex float64 transform
+// (z = target + i*est), because the 1e-4 tolerance on LSD / log-sispec needs ~float64 FFT accuracy
+// on hard-low-passed estimates (hard part 1).  After the transform the two
+// spectra are separated, rounded to complex64 like librosa's store, and every metric formula runs
+// in float32 exactly as torch does on the CPU; cross-frame sums are kept in float64.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "fft_core.cuh"
+#include "stft_tables.hpp"
+
+namespace ssr {
+
+std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+std::atomic<uint64_t>& launch_counter() {
+  static std::atomic<uint64_t> c{0};
+  return c;
+}
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxChunk = 64;   // frames per work item (upper bound)
+constexpr int kPartials = 8;    // doubles per work item
+constexpr int kSsimTR = 64;     // SSIM tile: output rows
+constexpr int kSsimTC = 128;    // SSIM tile: output cols (= threads)
+
+struct StftDev {
+  int n_fft, hop, F, M;
+  const cd* tw;            // exp(-2 pi i n / M)
+  const double* win_half;  // direct: 0.5 * window[n]
+  const uint16_t* ppos;    // direct: padded smem slot of frequency k after the DIF passes
+  const cd* cw;            // bluestein: 0.5 * window[n] * chirp[n]
+  const cd* bfilt;         // bluestein: FFT_M(conj chirp) / M in DIF (digit-reversed) order
+  const cd* cpost;         // bluestein: chirp[k]
+};
+
+}  // namespace ssr
+
+struct ssr_stft_plan {
+  int n_fft, hop, F, M, logM, bluestein, device;
+  void* blob;  // one device allocation holding all tables
+  ssr::StftDev dev;
+};
+
+namespace ssr {
+
+__host__ __device__ inline long long stft_frames(long long L, int n_fft, int hop) {
+  return 1 + (L + 2 * (n_fft / 2) - n_fft) / hop;
+}
+
+__device__ __forceinline__ long long reflect_index(long long i, long long L) {
+  if (i >= 0 && i < L) return i;
+  if (L == 1) return 0;
+  long long period = 2 * (L - 1);
+  i %= period;
+  if (i < 0) i += period;
+  return i < L ? i : period - i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup: work-item table.  item_start[p] = first work item of pair p (item = chunk of <= `chunk`
+// consecutive frames), item_pair[item] = p, spec_off[p] = first spectrogram element of pair p.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_setup(const long long* __restrict__ offsets, int n, int n_fft, int hop, int chunk,
+                        int F, int* __restrict__ item_start, int* __restrict__ item_pair,
+                        long long* __restrict__ spec_off) {
+  __shared__ long long s_items[1024], s_frames[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, t * per), hi = min(n, lo + per);
+  long long it = 0, fr = 0;
+  for (int p = lo; p < hi; ++p) {
+    long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
+    it += (T + chunk - 1) / chunk;
+    fr += T;
+  }
+  s_items[t] = it;
+  s_frames[t] = fr;
+  __syncthreads();
+  if (t == 0) {
+    long long a = 0, b = 0;
+    for (int i = 0; i < 1024; ++i) {
+      long long x = s_items[i], y = s_frames[i];
+      s_items[i] = a;
+      s_frames[i] = b;
+      a += x;
+      b += y;
+    }
+  }
+  __syncthreads();
+  it = s_items[t];
+  fr = s_frames[t];
+  for (int p = lo; p < hi; ++p) {
+    long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
+    int nc = (int)((T + chunk - 1) / chunk);
+    item_start[p] = (int)it;
+    spec_off[p] = fr * F;
+    for (int c = 0; c < nc; ++c) item_pair[it + c] = p;
+    it += nc;
+    fr += T;
+  }
+  if (hi == n) {
+    item_start[n] = (int)it;
+    spec_off[n] = fr * F;
+  }
+}
+
+struct SyncThreads {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: one CTA walks the frames of its work items; per frame:
+//   load (window folded in) -> forward FFT in shared memory [-> Bluestein filter -> inverse FFT]
+//   -> separate the two spectra -> complex64 rounding -> float32 magnitudes -> metric terms.
+// ---------------------------------------------------------------------------------------------
+template <int LOGM, bool BLUE>
+__global__ void __launch_bounds__(kThreads)
+k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict__ tgt,
+               const long long* __restrict__ offsets, const int* __restrict__ item_start,
+               const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
+               double* __restrict__ partials, float* __restrict__ spec_e,
+               float* __restrict__ spec_t, const long long* __restrict__ spec_off) {
+  constexpr int M = 1 << LOGM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* buf = reinterpret_cast<cd*>(smem_raw);
+  __shared__ float lsd_part[kMaxChunk][kWarps];
+  __shared__ double red[kWarps][kPartials];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = P.n_fft, F = P.F, hop = P.hop;
+  const bool want_lsd = flags & SSR_METRIC_LSD, want_log = flags & SSR_METRIC_LOG_SISPEC,
+             want_lin = flags & SSR_METRIC_SISPEC;
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int p = item_pair[item];
+    const int c = item - item_start[p];
+    const long long off = offsets[p];
+    const long long L = offsets[p + 1] - off;
+    const long long T = stft_frames(L, N, hop);
+    const long long f0 = (long long)c * chunk;
+    const int nf = (int)min((long long)chunk, T - f0);
+    const float* xe = est + off;
+    const float* xt = tgt + off;
+    double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
+
+    for (int fi = 0; fi < nf; ++fi) {
+      const long long f = f0 + fi;
+      const long long start = f * hop - N / 2;
+      // ---- load: z[n] = 0.5*w[n]*(target + i*est)  (Bluestein: times the chirp, zero padded)
+      if (!BLUE) {
+        for (int n = tid; n < M; n += kThreads) {
+          long long idx = reflect_index(start + n, L);
+          double w = P.win_half[n];
+          buf[pad_idx(n)] = cd{w * (double)__ldg(xt + idx), w * (double)__ldg(xe + idx)};
+        }
+      } else {
+        for (int n = tid; n < M; n += kThreads) {
+          cd v{0.0, 0.0};
+          if (n < N) {
+            long long idx = reflect_index(start + n, L);
+            double t = (double)__ldg(xt + idx), e = (double)__ldg(xe + idx);
+            cd w = P.cw[n];
+            v = cd{t * w.x - e * w.y, t * w.y + e * w.x};
+          }
+          buf[pad_idx(n)] = v;
+        }
+      }
+      __syncthreads();
+      fft_forward_dif<LOGM>(buf, P.tw, tid, kThreads, SyncThreads());
+      __syncthreads();
+      if (BLUE) {
+        for (int i = tid; i < M; i += kThreads) buf[pad_idx(i)] = cmul(buf[pad_idx(i)], P.bfilt[i]);
+        __syncthreads();
+        fft_inverse_dit<LOGM>(buf, P.tw, tid, kThreads, SyncThreads());
+        __syncthreads();
+      }
+      // ---- epilogue over the F = n_fft/2+1 bins
+      float lsd_acc = 0.f, pet = 0.f, ptt = 0.f, pee = 0.f, qet = 0.f, qtt = 0.f, qee = 0.f;
+      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
+      float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
+      for (int k = tid; k < F; k += kThreads) {
+        cd a, b;
+        if (!BLUE) {
+          a = buf[P.ppos[k]];
+          b = buf[P.ppos[(N - k) & (N - 1)]];
+        } else {
+          int k2 = k ? N - k : 0;
+          a = cmul(buf[pad_idx(k)], P.cpost[k]);
+          b = cmul(buf[pad_idx(k2)], P.cpost[k2]);
+        }
+        // T = (Z[k] + conj Z[N-k]) / 2,  E = (Z[k] - conj Z[N-k]) / (2i); the 1/2 is in the window
+        float tre = (float)(a.x + b.x), tim = (float)(a.y - b.y);
+        float ere = (float)(a.y + b.y), eim = (float)(b.x - a.x);
+        float mt = sqrtf(tre * tre + tim * tim);
+        float me = sqrtf(ere * ere + eim * eim);
+        if (st) st[k] = mt;
+        if (se) se[k] = me;
+        if (want_lsd) {
+          float den = me + 1e-12f;
+          float q = (mt * mt) / (den * den) + 1e-12f;
+          float l = log10f(q);
+          lsd_acc += l * l;
+        }
+        if (want_lin) {
+          pet += me * mt;
+          ptt += mt * mt;
+          pee += me * me;
+        }
+        if (want_log) {
+          float le = log10f(me + 1e-12f), lt = log10f(mt + 1e-12f);
+          qet += le * lt;
+          qtt += lt * lt;
+          qee += le * le;
+        }
+      }
+      if (want_lsd) {
+        float w = warp_sum(lsd_acc);
+        if (lane == 0) lsd_part[fi][warp] = w;
+      }
+      s_et += (double)pet;
+      s_tt += (double)ptt;
+      s_ee += (double)pee;
+      l_et += (double)qet;
+      l_tt += (double)qtt;
+      l_ee += (double)qee;
+      __syncthreads();  // buf is rewritten by the next frame's load
+    }
+
+    // ---- per-item reduction -> partials[item][0..7]
+    double lsd_sum = 0.0;
+    if (want_lsd && tid < nf) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += lsd_part[tid][w];
+      lsd_sum = (double)sqrtf(s / (float)F);  // torch.mean(dim=3) ** 0.5 in float32
+    }
+    double v[7] = {lsd_sum, s_et, s_tt, s_ee, l_et, l_tt, l_ee};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      double r = warp_sum(v[i]);
+      if (lane == 0) red[warp][i] = r;
+    }
+    __syncthreads();
+    if (tid < 7) {
+      double r = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) r += red[w][tid];
+      partials[(size_t)item * kPartials + tid] = r;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: SSIM of two (T, F) float32 magnitude images, valid 7x7 windows only (skimage crops the
+// 3-pixel border, so the reflect boundary mode of uniform_filter never reaches the mean).
+// One CTA = one tile of kSsimTR x kSsimTC window positions; each thread owns one column and
+// slides down the rows keeping the last 7 horizontal 7-sums of (x, y, xx, yy, xy) in registers.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSsimTC)
+k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
+       const long long* __restrict__ spec_off, const long long* __restrict__ offsets, int pair0,
+       int n_fft, int hop, int F, int tiles_x, int tiles_per_pair, double* __restrict__ ssim_part) {
+  const int p = pair0 + blockIdx.y;
+  const int tile = blockIdx.x;
+  const int ty = tile / tiles_x, tx = tile % tiles_x;
+  const long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
+  const int rows_out = (int)T - 6, cols_out = F - 6;
+  const int r0 = ty * kSsimTR;
+  double* out = ssim_part + (size_t)p * tiles_per_pair + tile;
+  if (r0 >= rows_out || cols_out <= 0) {
+    if (threadIdx.x == 0) *out = 0.0;
+    return;
+  }
+  const int r_end = min(r0 + kSsimTR, rows_out) + 6;  // input rows [r0, r_end)
+  const int c0 = tx * kSsimTC;
+  const int c = threadIdx.x;
+  const bool col_ok = (c0 + c) < cols_out;
+  const float* E = spec_e + spec_off[p];
+  const float* G = spec_t + spec_off[p];
+  __shared__ float rowbuf[2][2][kSsimTC + 8];
+  __shared__ double red[kSsimTC / 32];
+
+  float hx[7], hy[7], hxx[7], hyy[7], hxy[7];
+#pragma unroll
+  for (int s = 0; s < 7; ++s) hx[s] = hy[s] = hxx[s] = hyy[s] = hxy[s] = 0.f;
+  float acc = 0.f;
+  const float inv49 = 1.0f / 49.0f, cov_norm = 49.0f / 48.0f;
+  const float C1 = 0.0004f, C2 = 0.0036f;  // (0.01*2)^2, (0.03*2)^2
+
+  for (int rb = r0; rb < r_end; rb += 7) {
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+      const int r = rb + s;
+      if (r < r_end) {  // uniform across the CTA
+        const int par = (r - r0) & 1;
+        const float* er = E + (long long)r * F;
+        const float* gr = G + (long long)r * F;
+        int col = c0 + c;
+        rowbuf[par][0][c] = col < F ? er[col] : 0.f;
+        rowbuf[par][1][c] = col < F ? gr[col] : 0.f;
+        if (c < 6) {
+          col = c0 + kSsimTC + c;
+          rowbuf[par][0][kSsimTC + c] = col < F ? er[col] : 0.f;
+          rowbuf[par][1][kSsimTC + c] = col < F ? gr[col] : 0.f;
+        }
+        __syncthreads();
+        float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          float x = rowbuf[par][0][c + j], y = rowbuf[par][1][c + j];
+          sx += x;
+          sy += y;
+          sxx += x * x;
+          syy += y * y;
+          sxy += x * y;
+        }
+        hx[s] = sx;
+        hy[s] = sy;
+        hxx[s] = sxx;
+        hyy[s] = syy;
+        hxy[s] = sxy;
+        if (r - r0 >= 6 && col_ok) {
+          float vx_ = 0.f, vy_ = 0.f, vxx = 0.f, vyy = 0.f, vxy_ = 0.f;
+#pragma unroll
+          for (int q = 0; q < 7; ++q) {
+            vx_ += hx[q];
+            vy_ += hy[q];
+            vxx += hxx[q];
+            vyy += hyy[q];
+            vxy_ += hxy[q];
+          }
+          float ux = vx_ * inv49, uy = vy_ * inv49;
+          float uxx = vxx * inv49, uyy = vyy * inv49, uxy = vxy_ * inv49;
+          float vx = cov_norm * (uxx - ux * ux);
+          float vy = cov_norm * (uyy - uy * uy);
+          float vxy = cov_norm * (uxy - ux * uy);
+          float A1 = 2.f * ux * uy + C1, A2 = 2.f * vxy + C2;
+          float B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+          acc += (A1 * A2) / (B1 * B2);
+        }
+      }
+    }
+  }
+  double r = warp_sum((double)acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = r;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kSsimTC / 32; ++w) s += red[w];
+    *out = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: fixed-order sum of the per-item partials -> the four metrics of each pair (float64).
+// ---------------------------------------------------------------------------------------------
+__device__ inline double sispec_from_sums(double s_et, double s_tt, double s_ee) {
+  const double EPS = 1e-12;
+  double alpha = s_et / (s_tt + EPS);            // energy_unify: target' = alpha * target
+  double tt = alpha * alpha * s_tt;              // ||target'||^2
+  double nn = s_ee - 2.0 * alpha * s_et + tt;    // ||est - target'||^2
+  if (nn < 0.0) nn = 0.0;
+  return 10.0 * log10(tt / (nn + EPS) + EPS);
+}
+
+__global__ void k_finalize(const long long* __restrict__ offsets, int n, int n_fft, int hop, int F,
+                           const int* __restrict__ item_start, const double* __restrict__ partials,
+                           const double* __restrict__ ssim_part, int tiles_per_pair, unsigned flags,
+                           double* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int it = item_start[p]; it < item_start[p + 1]; ++it)
+    for (int i = 0; i < 7; ++i) v[i] += partials[(size_t)it * kPartials + i];
+  out[p * 4 + 0] = (flags & SSR_METRIC_LSD) ? v[0] / (double)T : nan;
+  out[p * 4 + 1] = (flags & SSR_METRIC_LOG_SISPEC) ? sispec_from_sums(v[4], v[5], v[6]) : nan;
+  out[p * 4 + 2] = (flags & SSR_METRIC_SISPEC) ? sispec_from_sums(v[1], v[2], v[3]) : nan;
+  if (flags & SSR_METRIC_SSIM) {
+    double s = 0.0;
+    for (int t = 0; t < tiles_per_pair; ++t) s += ssim_part[(size_t)p * tiles_per_pair + t];
+    double cnt = (double)(T - 6) * (double)(F - 6);
+    out[p * 4 + 3] = (T > 6 && F > 6) ? s / cnt : nan;
+  } else {
+    out[p * 4 + 3] = nan;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct WsLayout {
+  size_t item_start, item_pair, spec_off, partials, ssim_part, spec_e, spec_t, total;
+  int chunk, n_items, tiles_x, tiles_per_pair;
+  long long total_frames;
+};
+
+static int plan_layout(const ssr_stft_plan* plan, const int64_t* offs, int n, unsigned flags,
+                       bool need_spec_t_only, WsLayout* w) {
+  long long total_frames = 0, max_T = 0;
+  for (int p = 0; p < n; ++p) {
+    long long L = offs[p + 1] - offs[p];
+    if (L < 1) return fail(SSR_ERR_INVALID, "empty utterance in batch");
+    long long T = stft_frames(L, plan->n_fft, plan->hop);
+    total_frames += T;
+    if (T > max_T) max_T = T;
+  }
+  // aim for ~8 work items per resident CTA slot (148 SMs x 2), bounded to [4, kMaxChunk] frames
+  long long want = 148LL * 2 * 8;
+  long long chunk = (total_frames + want - 1) / want;
+  if (chunk < 4) chunk = 4;
+  if (chunk > kMaxChunk) chunk = kMaxChunk;
+  long long n_items = 0;
+  for (int p = 0; p < n; ++p) {
+    long long T = stft_frames(offs[p + 1] - offs[p], plan->n_fft, plan->hop);
+    n_items += (T + chunk - 1) / chunk;
+  }
+  if (n_items > 0x7fffffffLL) return fail(SSR_ERR_INVALID, "batch too large");
+  w->chunk = (int)chunk;
+  w->n_items = (int)n_items;
+  w->total_frames = total_frames;
+  w->tiles_x = (plan->F - 6 + kSsimTC - 1) / kSsimTC;
+  if (w->tiles_x < 1) w->tiles_x = 1;
+  long long rows = max_T - 6;
+  int tiles_y = rows > 0 ? (int)((rows + kSsimTR - 1) / kSsimTR) : 1;
+  w->tiles_per_pair = w->tiles_x * tiles_y;
+  size_t o = 0;
+  w->item_start = o;
+  o = align_up(o + sizeof(int) * (size_t)(n + 1), 256);
+  w->item_pair = o;
+  o = align_up(o + sizeof(int) * (size_t)n_items, 256);
+  w->spec_off = o;
+  o = align_up(o + sizeof(long long) * (size_t)(n + 1), 256);
+  w->partials = o;
+  o = align_up(o + sizeof(double) * kPartials * (size_t)n_items, 256);
+  w->ssim_part = o;
+  if (flags & SSR_METRIC_SSIM) o = align_up(o + sizeof(double) * (size_t)n * w->tiles_per_pair, 256);
+  w->spec_e = o;
+  if (flags & SSR_METRIC_SSIM) o = align_up(o + sizeof(float) * (size_t)total_frames * plan->F, 256);
+  w->spec_t = o;
+  if ((flags & SSR_METRIC_SSIM) && !need_spec_t_only)
+    o = align_up(o + sizeof(float) * (size_t)total_frames * plan->F, 256);
+  w->total = o;
+  return SSR_OK;
+}
+
+template <int LOGM, bool BLUE>
+static int launch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStream_t st,
+                     const float* est, const float* tgt, const long long* offs_dev,
+                     const int* item_start, const int* item_pair, int n_items, int chunk,
+                     unsigned flags, double* partials, float* spec_e, float* spec_t,
+                     const long long* spec_off) {
+  auto kern = k_stft_metrics<LOGM, BLUE>;
+  SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, n_items,
+                                     chunk, flags, partials, spec_e, spec_t, spec_off);
+  SSR_LAUNCH_CHECK("k_stft_metrics");
+  return SSR_OK;
+}
+
+template <bool BLUE>
+static int dispatch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStream_t st,
+                       const float* est, const float* tgt, const long long* offs_dev,
+                       const int* item_start, const int* item_pair, int n_items, int chunk,
+                       unsigned flags, double* partials, float* spec_e, float* spec_t,
+                       const long long* spec_off) {
+#define SSR_CASE(LM)                                                                            \
+  case LM:                                                                                      \
+    return launch_k1<LM, BLUE>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair, \
+                               n_items, chunk, flags, partials, spec_e, spec_t, spec_off);
+  switch (plan->logM) {
+    SSR_CASE(8)
+    SSR_CASE(9)
+    SSR_CASE(10)
+    SSR_CASE(11)
+    SSR_CASE(12)
+    SSR_CASE(13)
+    default:
+      return fail(SSR_ERR_INVALID, "unsupported FFT size");
+  }
+#undef SSR_CASE
+}
+
+static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st, const float* est,
+                  const float* tgt, const long long* offs_dev, int n, unsigned flags,
+                  unsigned char* ws, float* spec_e, float* spec_t) {
+  int* item_start = reinterpret_cast<int*>(ws + w.item_start);
+  int* item_pair = reinterpret_cast<int*>(ws + w.item_pair);
+  long long* spec_off = reinterpret_cast<long long*>(ws + w.spec_off);
+  double* partials = reinterpret_cast<double*>(ws + w.partials);
+  k_setup<<<1, 1024, 0, st>>>(offs_dev, n, plan->n_fft, plan->hop, w.chunk, plan->F, item_start,
+                              item_pair, spec_off);
+  SSR_LAUNCH_CHECK("k_setup");
+  size_t smem = sizeof(cd) * (size_t)padded_size(plan->M);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = (int)((200 * 1024) / (smem + 4096));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  int grid = sms * per_sm;
+  if (grid > w.n_items) grid = w.n_items;
+  if (plan->bluestein)
+    return dispatch_k1<true>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair,
+                             w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off);
+  return dispatch_k1<false>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair,
+                            w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off);
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+extern "C" {
+
+int ssr_version(void) { return 100; }
+const char* ssr_last_error(void) { return last_error_ref().c_str(); }
+uint64_t ssr_launch_count(void) { return launch_counter().load(); }
+
+int ssr_stft_plan_create(ssr_stft_plan** out, int n_fft, int hop, const double* window_host) {
+  if (!out) return fail(SSR_ERR_INVALID, "plan pointer is NULL");
+  *out = nullptr;
+  if (n_fft < 65 || n_fft > 8192) return fail(SSR_ERR_INVALID, "n_fft must be in [65, 8192]");
+  if (hop < 1) return fail(SSR_ERR_INVALID, "hop must be >= 1");
+  StftTables tb;
+  if (!build_stft_tables(n_fft, window_host, &tb))
+    return fail(SSR_ERR_INVALID, "n_fft too large for the Bluestein path (max 4096)");
+  const int M = tb.M, logM = tb.logM;
+  const bool blue = tb.bluestein;
+  size_t o = 0;
+  size_t o_tw = o;
+  o = align_up(o + sizeof(cd) * (size_t)M, 256);
+  size_t o_win = o;
+  o = align_up(o + sizeof(double) * (size_t)n_fft, 256);
+  size_t o_pos = o;
+  o = align_up(o + sizeof(uint16_t) * (size_t)M, 256);
+  size_t o_cw = o;
+  o = align_up(o + sizeof(cd) * (size_t)n_fft, 256);
+  size_t o_bf = o;
+  o = align_up(o + sizeof(cd) * (size_t)M, 256);
+  size_t o_cp = o;
+  o = align_up(o + sizeof(cd) * (size_t)n_fft, 256);
+  std::vector<unsigned char> host(o, 0);
+  memcpy(host.data() + o_tw, tb.tw.data(), sizeof(cd) * (size_t)M);
+  memcpy(host.data() + o_win, tb.win_half.data(), sizeof(double) * (size_t)n_fft);
+  memcpy(host.data() + o_pos, tb.ppos.data(), sizeof(uint16_t) * (size_t)M);
+  memcpy(host.data() + o_cw, tb.cw.data(), sizeof(cd) * (size_t)n_fft);
+  memcpy(host.data() + o_bf, tb.bfilt.data(), sizeof(cd) * (size_t)M);
+  memcpy(host.data() + o_cp, tb.cpost.data(), sizeof(cd) * (size_t)n_fft);
+  ssr_stft_plan* p = new ssr_stft_plan();
+  p->n_fft = n_fft;
+  p->hop = hop;
+  p->F = n_fft / 2 + 1;
+  p->M = M;
+  p->logM = logM;
+  p->bluestein = blue ? 1 : 0;
+  p->blob = nullptr;
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaMalloc(&p->blob, o);
+  if (e == cudaSuccess) e = cudaMemcpy(p->blob, host.data(), o, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (p->blob) cudaFree(p->blob);
+    delete p;
+    return fail(SSR_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+  }
+  unsigned char* d = static_cast<unsigned char*>(p->blob);
+  p->dev.n_fft = n_fft;
+  p->dev.hop = hop;
+  p->dev.F = p->F;
+  p->dev.M = M;
+  p->dev.tw = reinterpret_cast<const cd*>(d + o_tw);
+  p->dev.win_half = reinterpret_cast<const double*>(d + o_win);
+  p->dev.ppos = reinterpret_cast<const uint16_t*>(d + o_pos);
+  p->dev.cw = reinterpret_cast<const cd*>(d + o_cw);
+  p->dev.bfilt = reinterpret_cast<const cd*>(d + o_bf);
+  p->dev.cpost = reinterpret_cast<const cd*>(d + o_cp);
+  *out = p;
+  return SSR_OK;
+}
+
+int ssr_stft_plan_destroy(ssr_stft_plan* plan) {
+  if (!plan) return SSR_OK;
+  if (plan->blob) cudaFree(plan->blob);
+  delete plan;
+  return SSR_OK;
+}
+
+int64_t ssr_stft_num_frames(const ssr_stft_plan* plan, int64_t length) {
+  return plan ? (int64_t)stft_frames(length, plan->n_fft, plan->hop) : -1;
+}
+
+size_t ssr_stft_metrics_workspace_bytes(const ssr_stft_plan* plan, const int64_t* offsets_host,
+                                        int n_pairs, unsigned flags) {
+  if (!plan || !offsets_host || n_pairs < 1) return 0;
+  WsLayout w;
+  if (plan_layout(plan, offsets_host, n_pairs, flags, false, &w) != SSR_OK) return 0;
+  return w.total;
+}
+
+int ssr_stft_metrics_batched(const ssr_stft_plan* plan, const float* est_dev, const float* tgt_dev,
+                             const int64_t* offsets_host, const int64_t* offsets_dev, int n_pairs,
+                             unsigned flags, double* out_dev, void* workspace_dev,
+                             size_t workspace_bytes, void* stream) {
+  if (!plan || !est_dev || !tgt_dev || !offsets_host || !offsets_dev || !out_dev || n_pairs < 1)
+    return fail(SSR_ERR_INVALID, "ssr_stft_metrics_batched: bad argument");
+  if (flags & ~SSR_METRIC_ALL) return fail(SSR_ERR_INVALID, "unknown metric flag");
+  WsLayout w;
+  int rc = plan_layout(plan, offsets_host, n_pairs, flags, false, &w);
+  if (rc != SSR_OK) return rc;
+  if (!workspace_dev || workspace_bytes < w.total)
+    return fail(SSR_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned char* ws = static_cast<unsigned char*>(workspace_dev);
+  const long long* offs = reinterpret_cast<const long long*>(offsets_dev);
+  const bool do_ssim = flags & SSR_METRIC_SSIM;
+  float* spec_e = do_ssim ? reinterpret_cast<float*>(ws + w.spec_e) : nullptr;
+  float* spec_t = do_ssim ? reinterpret_cast<float*>(ws + w.spec_t) : nullptr;
+  rc = run_k1(plan, w, st, est_dev, tgt_dev, offs, n_pairs, flags, ws, spec_e, spec_t);
+  if (rc != SSR_OK) return rc;
+  double* ssim_part = reinterpret_cast<double*>(ws + w.ssim_part);
+  if (do_ssim) {
+    for (int p0 = 0; p0 < n_pairs; p0 += 32768) {
+      int np = n_pairs - p0 < 32768 ? n_pairs - p0 : 32768;
+      dim3 grid(w.tiles_per_pair, np);
+      k_ssim<<<grid, kSsimTC, 0, st>>>(spec_e, spec_t, reinterpret_cast<long long*>(ws + w.spec_off),
+                                       offs, p0, plan->n_fft, plan->hop, plan->F, w.tiles_x,
+                                       w.tiles_per_pair, ssim_part);
+      SSR_LAUNCH_CHECK("k_ssim");
+    }
+  }
+  k_finalize<<<(n_pairs + 127) / 128, 128, 0, st>>>(
+      offs, n_pairs, plan->n_fft, plan->hop, plan->F, reinterpret_cast<int*>(ws + w.item_start),
+      reinterpret_cast<double*>(ws + w.partials), ssim_part, w.tiles_per_pair, flags, out_dev);
+  SSR_LAUNCH_CHECK("k_finalize");
+  return SSR_OK;
+}
+
+int ssr_stft_magnitude_batched(const ssr_stft_plan* plan, const float* x_dev,
+                               const int64_t* offsets_host, const int64_t* offsets_dev, int n,
+                               float* spec_dev, void* workspace_dev, size_t workspace_bytes,
+                               void* stream) {
+  if (!plan || !x_dev || !offsets_host || !offsets_dev || !spec_dev || n < 1)
+    return fail(SSR_ERR_INVALID, "ssr_stft_magnitude_batched: bad argument");
+  WsLayout w;
+  int rc = plan_layout(plan, offsets_host, n, 0, false, &w);
+  if (rc != SSR_OK) return rc;
+  if (!workspace_dev || workspace_bytes < w.total)
+    return fail(SSR_ERR_WORKSPACE, "workspace too small");
+  return run_k1(plan, w, static_cast<cudaStream_t>(stream), x_dev, x_dev,
+                reinterpret_cast<const long long*>(offsets_dev), n, 0,
+                static_cast<unsigned char*>(workspace_dev), nullptr, spec_dev);
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+// host_emul.cu -- CPU emulation of the shared-memory FFT core and the K1 per-frame pipeline
+// (direct and Bluestein), so index math and tables are validated without a GPU.
+// Build: make build/host_emul ; run: build/host_emul  (exit code 0 = all checks passed)
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "../ssr_eval_b200/csrc/stft_tables.hpp"
+
+using namespace ssr;
+
+static const int NT = 256;  // emulated threads
+struct NoSync {
+  void operator()() const {}
+};
+
+// The passes are written for lock-step threads with a barrier between passes; emulate by running
+// pass s for all threads before pass s+1.
+template <int LOGM, typename T>
+static void emu_forward(C2<T>* buf, const C2<T>* tw) {
+  constexpr int M = 1 << LOGM;
+  int N = M;
+  for (int s = 0; s < n_r8(LOGM) + n_r4(LOGM); ++s) {
+    for (int tid = 0; tid < NT; ++tid) {
+      if (s < n_r8(LOGM)) dif_pass<8>(buf, M, N, tw, tid, NT);
+      else dif_pass<4>(buf, M, N, tw, tid, NT);
+    }
+    N /= (s < n_r8(LOGM)) ? 8 : 4;
+  }
+}
+template <int LOGM, typename T>
+static void emu_inverse(C2<T>* buf, const C2<T>* tw) {
+  constexpr int M = 1 << LOGM;
+  int N = 1;
+  for (int s = n_r8(LOGM) + n_r4(LOGM) - 1; s >= 0; --s) {
+    N *= (s < n_r8(LOGM)) ? 8 : 4;
+    for (int tid = 0; tid < NT; ++tid) {
+      if (s < n_r8(LOGM)) dit_pass<8>(buf, M, N, tw, tid, NT);
+      else dit_pass<4>(buf, M, N, tw, tid, NT);
+    }
+  }
+}
+
+static double frand() { return (double)rand() / RAND_MAX * 2.0 - 1.0; }
+
+template <int LOGM>
+static int check_fft() {
+  constexpr int M = 1 << LOGM;
+  std::vector<cd> tw(M), buf(padded_size(M)), x(M);
+  for (int n = 0; n < M; ++n) {
+    long double a = -2 * kPiL * n / M;
+    tw[n] = cd{(double)cosl(a), (double)sinl(a)};
+    x[n] = cd{frand(), frand()};
+    buf[pad_idx(n)] = x[n];
+  }
+  emu_forward<LOGM, double>(buf.data(), tw.data());
+  double maxerr = 0;
+  for (int k = 0; k < M; k += (M > 1024 ? 37 : 1)) {
+    long double re = 0, im = 0;
+    for (int n = 0; n < M; ++n) {
+      long double a = -2 * kPiL * ((long long)n * k % M) / M;
+      re += x[n].x * cosl(a) - x[n].y * sinl(a);
+      im += x[n].x * sinl(a) + x[n].y * cosl(a);
+    }
+    cd v = buf[pad_idx(dif_position(k, LOGM))];
+    maxerr = fmax(maxerr, fmax(fabs(v.x - (double)re), fabs(v.y - (double)im)));
+  }
+  emu_inverse<LOGM, double>(buf.data(), tw.data());
+  double rt = 0;
+  for (int n = 0; n < M; ++n)
+    rt = fmax(rt, fmax(fabs(buf[pad_idx(n)].x / M - x[n].x), fabs(buf[pad_idx(n)].y / M - x[n].y)));
+  printf("fft M=%5d  forward maxerr %.3e  roundtrip maxerr %.3e\n", M, maxerr, rt);
+  return (maxerr < 1e-10 && rt < 1e-12) ? 0 : 1;
+}
+
+// emulate K1's per-frame work for one frame of (t, e) and compare T[k], E[k] with a direct DFT
+template <int LOGM>
+static int check_frame(int n_fft) {
+  constexpr int M = 1 << LOGM;
+  StftTables tb;
+  if (!build_stft_tables(n_fft, nullptr, &tb) || tb.logM != LOGM) {
+    printf("table build failed for n_fft=%d (logM %d)\n", n_fft, tb.logM);
+    return 1;
+  }
+  const int N = n_fft, F = N / 2 + 1;
+  std::vector<float> t(N), e(N);
+  for (int n = 0; n < N; ++n) {
+    t[n] = (float)frand();
+    e[n] = (float)(1e-6 * frand());
+  }
+  std::vector<cd> buf(padded_size(M));
+  if (!tb.bluestein) {
+    for (int n = 0; n < M; ++n) buf[pad_idx(n)] = cd{tb.win_half[n] * t[n], tb.win_half[n] * e[n]};
+    emu_forward<LOGM, double>(buf.data(), tb.tw.data());
+  } else {
+    for (int n = 0; n < M; ++n) {
+      cd v{0, 0};
+      if (n < N) v = cd{t[n] * tb.cw[n].x - e[n] * tb.cw[n].y, t[n] * tb.cw[n].y + e[n] * tb.cw[n].x};
+      buf[pad_idx(n)] = v;
+    }
+    emu_forward<LOGM, double>(buf.data(), tb.tw.data());
+    for (int i = 0; i < M; ++i) buf[pad_idx(i)] = cmul(buf[pad_idx(i)], tb.bfilt[i]);
+    emu_inverse<LOGM, double>(buf.data(), tb.tw.data());
+  }
+  double errT = 0, errE = 0, magT = 0, magE = 0;
+  for (int k = 0; k < F; ++k) {
+    cd a, b;
+    if (!tb.bluestein) {
+      a = buf[tb.ppos[k]];
+      b = buf[tb.ppos[(N - k) & (N - 1)]];
+    } else {
+      int k2 = k ? N - k : 0;
+      a = cmul(buf[pad_idx(k)], tb.cpost[k]);
+      b = cmul(buf[pad_idx(k2)], tb.cpost[k2]);
+    }
+    double tre = a.x + b.x, tim = a.y - b.y, ere = a.y + b.y, eim = b.x - a.x;
+    long double rt = 0, it = 0, re_ = 0, ie = 0;
+    for (int n = 0; n < N; ++n) {
+      long double w = 0.5L - 0.5L * cosl(2 * kPiL * n / N);
+      long double ang = -2 * kPiL * ((long long)n * k % N) / N;
+      long double c = cosl(ang), s = sinl(ang);
+      rt += w * t[n] * c;
+      it += w * t[n] * s;
+      re_ += w * e[n] * c;
+      ie += w * e[n] * s;
+    }
+    errT = fmax(errT, fmax(fabs(tre - (double)rt), fabs(tim - (double)it)));
+    errE = fmax(errE, fmax(fabs(ere - (double)re_), fabs(eim - (double)ie)));
+    magT = fmax(magT, hypot((double)rt, (double)it));
+    magE = fmax(magE, hypot((double)re_, (double)ie));
+  }
+  printf("frame n_fft=%4d M=%4d %s  |T|max %.3e err %.3e   |E|max %.3e err %.3e\n", N, M,
+         tb.bluestein ? "bluestein" : "direct   ", magT, errT, magE, errE);
+  return (errT < 1e-11 * (1 + magT) && errE < 1e-11 * (1 + magT)) ? 0 : 1;
+}
+
+int main() {
+  int bad = 0;
+  bad += check_fft<8>();
+  bad += check_fft<9>();
+  bad += check_fft<10>();
+  bad += check_fft<11>();
+  bad += check_fft<12>();
+  bad += check_fft<13>();
+  bad += check_frame<8>(256);
+  bad += check_frame<10>(1024);
+  bad += check_frame<11>(2048);
+  bad += check_frame<12>(4096);
+  bad += check_frame<8>(65);
+  bad += check_frame<11>(743);
+  bad += check_frame<12>(1114);
+  bad += check_frame<13>(2229);
+  bad += check_frame<10>(371);
+  printf(bad ? "FAILED (%d)\n" : "ALL OK\n", bad);
+  return bad ? 1 : 0;
+}
