@@ -7,7 +7,7 @@ OBJ := build/obj
 LIB := ssr_eval_b200/lib/libssr_b200.so
 SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu
 OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(SRCS))
-HDRS := $(SRC)/common.cuh $(SRC)/fft_core.cuh $(SRC)/stft_tables.hpp include/ssr_b200.h
+HDRS := $(SRC)/common.cuh $(SRC)/fft_core.cuh $(SRC)/stft_tables.hpp $(SRC)/k1_map.cuh include/ssr_b200.h
 
 all: $(LIB)
 
@@ -20,7 +20,7 @@ $(LIB): $(OBJS)
 	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -cudart static
 
 # host-side emulation harness for the FFT core (no GPU needed)
-build/host_emul: tests/host_emul.cu $(SRC)/fft_core.cuh
+build/host_emul: tests/host_emul.cu $(SRC)/fft_core.cuh $(SRC)/stft_tables.hpp $(SRC)/k1_map.cuh
 	@mkdir -p build
 	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -o $@ $<
 

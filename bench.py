@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- utterance-pairs/s of the fused STFT+LSD hot path (BASELINE.json config[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+Workload (N=1): 1024 synthetic 48 kHz pairs, L = 240000 samples (5 s), n_fft 2048 / hop 512, LSD
+(BASELINE.json configs[1]).  A step = one pass of the hot path over that batch.  For N>1 every rank
+owns its own 1024 pairs (weak scaling) and the step ends with ONE NCCL all-reduce of the scalar
+metric accumulators.  Inputs (1.97 GB per rank) are far larger than the 126 MB L2, so no flush is
+needed between iterations.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_FFT, HOP, SR, LENGTH = 2048, 512, 48000, 240000
+METRIC = "utterance_pairs_per_sec_stft_lsd_48k_5s"
+UNIT = "pairs/s"
+
+
+def algorithmic_bytes(n_pairs, length):
+    """every sample of est and target read once + 32 B of results per pair."""
+    return n_pairs * (2 * length * 4 + 32)
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restated reference algorithm) on the host cores
+# --------------------------------------------------------------------------------------------
+_cpu_data = None
+
+
+_cpu_barrier = None
+
+
+def _cpu_init(barrier):
+    global _cpu_data, _cpu_barrier
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import torch
+    torch.set_num_threads(1)
+    import oracle  # noqa: F401
+    _cpu_barrier = barrier
+    rng = np.random.default_rng(os.getpid())
+    waves = []
+    for s in range(2):  # the CPU cost of STFT+LSD does not depend on the sample values
+        t = (0.1 * rng.standard_normal(LENGTH)).astype(np.float32)
+        e = (t + 1e-3 * rng.standard_normal(LENGTH)).astype(np.float32)
+        waves.append((e, t))
+    _cpu_data = waves
+
+
+def _cpu_warm(_):
+    _cpu_work(1)
+    _cpu_barrier.wait()  # every worker takes exactly one warm-up task
+    return 0
+
+
+def _cpu_work(n):
+    import oracle
+    acc = 0.0
+    for i in range(n):
+        e, t = _cpu_data[i % len(_cpu_data)]
+        acc += oracle.evaluation(e, t, n_fft=N_FFT, hop=HOP, which=("lsd",))["lsd"]
+    return acc
+
+
+class CpuArm:
+    """Persistent process pool, one worker per host core, each running the oracle's
+    STFT(float64 pocketfft)+LSD(torch float32) on 5 s pairs."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        self.cores = cores or os.cpu_count() or 1
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_init, initargs=(ctx.Barrier(self.cores),))
+        self.pool.map(_cpu_warm, range(self.cores), chunksize=1)  # imports + caches warm in EVERY worker
+
+    def step(self, pairs_per_core):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_work, [pairs_per_core] * self.cores, chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arm = CpuArm()
+    per_core = args.cpu_pairs_per_core
+    for _ in range(args.warmup):
+        arm.step(per_core)
+    t = sum(arm.step(per_core) for _ in range(args.steps))
+    arm.close()
+    pairs = per_core * arm.cores * args.steps
+    value = pairs / t
+    sample = "%d pairs/step (%d per core) of the N=1 workload, oracle STFT(f64)+LSD(f32)" % (per_core * arm.cores, per_core)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 48kHz 5s pairs, n_fft 2048 hop 512, STFT+LSD", "sample_rate": SR,
+                   "length": LENGTH, "n_fft": N_FFT, "hop": HOP},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_gpu_batch(n_pairs, device, rank):
+    """Synthetic batch built ON the device from 16 seeded CPU utterances: target = shifted / scaled
+    base utterance + a little noise; est = the repo's own STFT hard low-pass (cutoff 12 kHz) of it --
+    the parity-critical kind of estimate."""
+    import torch
+    from ssr_eval_b200.engine import HardLowpass, offsets_of
+    from ssr_eval_b200.synth import speech_like
+    base = torch.from_numpy(np.stack([speech_like(LENGTH, sr=SR, seed=5000 + 16 * rank + i) for i in range(16)])).to(device)
+    g = torch.Generator(device=device)
+    g.manual_seed(1234 + rank)
+    tgt = torch.empty(n_pairs * LENGTH, dtype=torch.float32, device=device)
+    for i in range(n_pairs):
+        shift = int(torch.randint(0, LENGTH, (1,), generator=g, device=device))
+        gain = 0.5 + 0.5 * float(torch.rand(1, generator=g, device=device))
+        seg = torch.roll(base[i % 16], shift) * gain
+        seg = seg + 1e-4 * torch.randn(LENGTH, generator=g, device=device)
+        tgt[i * LENGTH:(i + 1) * LENGTH] = seg
+    off = offsets_of([LENGTH] * n_pairs)
+    lp = HardLowpass(2048, 441)
+    est = lp.apply_device(tgt, off, [lp.cut_bin(12000 / (SR / 2))] * n_pairs)
+    torch.cuda.synchronize()
+    return est, tgt, off
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as td
+    from ssr_eval_b200 import _native as N
+    from ssr_eval_b200.engine import StftMetrics
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    n_pairs = args.pairs
+    est, tgt, off = make_gpu_batch(n_pairs, dev, rank)
+    off_dev = torch.from_numpy(off).to(dev)
+    eng = StftMetrics(N_FFT, HOP)
+    out = torch.empty((n_pairs, 4), dtype=torch.float64, device=dev)
+    flags = N.METRIC_LSD
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def step():
+        eng.metrics_device(est, tgt, off, flags, offsets_dev=off_dev, out=out)
+        if world > 1:  # the single all-reduce of the scalar metric accumulators (sum, count)
+            acc[0] = out[:, 0].sum()
+            acc[1] = float(n_pairs)
+            td.all_reduce(acc)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # ---- device-resident timing: exactly K steps, CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    N.timing_enable(True)
+    N.timing_collect()
+    launches0 = N.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = N.launch_count() - launches0
+    k1_ms, k1_n = N.timing_collect()
+    N.timing_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n_pairs * args.steps / (ms * 1e-3)
+    lsd_mean = float(out[:, 0].mean().item())
+
+    # ---- end to end through the public host API: pinned host buffers -> H2D -> kernels -> D2H
+    from ssr_eval_b200.engine import HostPipeline
+    est_h = est.cpu().pin_memory()
+    tgt_h = tgt.cpu().pin_memory()
+    pipe = HostPipeline(eng, n_pairs, LENGTH)
+    pipe.run(est_h, tgt_h, off, flags)  # warm
+    barrier()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = pipe.run(est_h, tgt_h, off, flags)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    e2e_value = world * n_pairs * e2e_steps / float(t.item())
+    assert abs(float(np.mean(res[:, 0])) - lsd_mean) < 1e-9
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        k1_avg_ms = k1_ms / max(k1_n, 1)
+        achieved = algorithmic_bytes(n_pairs, LENGTH) / (k1_avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "k_stft_metrics_2048", "kernel_ms": k1_avg_ms,
+                    "kernel_share_of_step": k1_ms / ms if ms else None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "note": "float64 FFT: the FP64 pipe binds, not HBM (see DESIGN.md roofline section)"}
+        traffic_file = os.path.join(ROOT, "profiles", "k1_traffic_bytes.json")
+        if os.path.exists(traffic_file):
+            try:
+                roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            arm = CpuArm()
+            per_core = args.cpu_pairs_per_core
+            arm.step(1)
+            tt = arm.step(per_core)
+            arm.close()
+            cpu = {"value": per_core * arm.cores / tt, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                   "sample": "%d pairs (%d per core) of the same workload, oracle STFT(f64)+LSD(f32), one process per core"
+                             % (per_core * arm.cores, per_core)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d pairs/GPU, 48kHz 5s (L=240000), n_fft 2048 hop 512, fused STFT+LSD" % n_pairs,
+                       "pairs_per_gpu": n_pairs, "sample_rate": SR, "length": LENGTH, "n_fft": N_FFT, "hop": HOP,
+                       "l2_policy": "inputs (1.97 GB/GPU) larger than L2, no flush", "parallelism": "pairs sharded, 1 all-reduce"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * n_pairs * LENGTH * 4),
+                    "d2h_bytes_per_step": int(n_pairs * 4 * 8), "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "check": {"mean_lsd": lsd_mean},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--pairs", type=int, default=1024, help="pairs per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-pairs-per-core", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,13 @@ const char* ssr_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench accounting) */
 uint64_t ssr_launch_count(void);
 
+/* Optional device-side timing of the dominant kernel (k_stft_metrics): when enabled, every launch is
+ * bracketed by CUDA events ON THE STREAM IT IS LAUNCHED ON.  ssr_timing_collect synchronises those
+ * events, returns the summed kernel milliseconds and the number of launches since the last
+ * collect, and resets.  Used by bench.py for the roofline line; off by default. */
+int ssr_timing_enable(int on);
+int ssr_timing_collect(double* total_ms, int* n_launches);
+
 /* ------------------------------------------------------------------------------------------
  * K1 + K2: batched STFT -> magnitude -> {LSD, log-sispec, sispec, SSIM}
  * Replaces AudioMetrics.__init__/wav_to_spectrogram/lsd/sispec/ssim and the metric half of

@@ -37,7 +37,7 @@ Pinning status (see DESIGN.md, section "Oracle")
 from .stft import hann_periodic, stft_complex, stft_mag, n_frames  # noqa: F401
 from .metrics import (  # noqa: F401
     EPS, AudioMetricsOracle, lsd, sispec, to_log, energy_unify, pow_norm, pow_p_norm,
-    ssim_skimage, evaluation, dict_mean,
+    ssim_skimage, evaluation, evaluation_exact_reductions, dict_mean,
 )
 from .lowpass import (  # noqa: F401
     TorchlibrosaSTFT, TorchlibrosaISTFT, FDomainHelperOracle, stft_hard_lowpass_v0,

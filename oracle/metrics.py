@@ -133,6 +133,29 @@ def evaluation(est, target, rate=None, n_fft=None, hop=None, which=("lsd", "log_
     return m.evaluation(est, target, None, which=which)
 
 
+def evaluation_exact_reductions(est, target, n_fft, hop):
+    """Secondary checker: the SAME float32 spectrograms and float32 element-wise formulas as the
+    reference, but every reduction (sum / mean / norm) carried out in float64.  The reference's
+    float32 reductions over T*F ~ 5e5 elements are themselves ~1e-5 relative noisy (4.5e-4 dB on
+    sispec at L = 240000, DESIGN.md "Numerics"), so this is the tighter statement of what the
+    formulas mean; the CUDA path (float64 accumulators) must agree with it to ~1e-6."""
+    n = min(len(est), len(target))
+    T = torch.tensor(stft_mag(np.asarray(target[:n], np.float32), n_fft, hop))
+    E = torch.tensor(stft_mag(np.asarray(est[:n], np.float32), n_fft, hop))
+    out = {}
+    term = (torch.log10(T ** 2 / ((E + EPS) ** 2) + EPS) ** 2).double()   # float32 element-wise
+    out["lsd"] = float(torch.mean(torch.mean(term, dim=1) ** 0.5))
+
+    def _sispec64(e, t):
+        s_et, s_tt = (e * t).sum(), (t * t).sum()
+        tp = s_et * t / (s_tt + EPS)
+        nn = ((e - tp) ** 2).sum()
+        return float(10 * torch.log10((tp ** 2).sum() / (nn + EPS) + EPS))
+    out["log_sispec"] = _sispec64(torch.log10(E + 1e-12).double(), torch.log10(T + 1e-12).double())
+    out["sispec"] = _sispec64(E.double(), T.double())
+    return out
+
+
 def dict_mean(dict_list):
     """ssr_eval/utils.py:24-28 (numpy float64 mean per key)."""
     return {k: np.mean([d[k] for d in dict_list]) for k in dict_list[0].keys()}

@@ -91,9 +91,56 @@ SSR_HD void bfly8(C2<T>* x) {
   x[7] = csub(e3, t3);
 }
 
+// multiply by W16^e (forward) / W16^-e (inverse), e in {1,2,3,6,9}; W16^4 = -+i is mul_mi
+template <bool INV, int E, typename T>
+SSR_HD C2<T> mul_w16(C2<T> v) {
+  const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173;  // cos, sin(pi/8)
+  const T h = (T)0.70710678118654752440;
+  // W16^e = cos(e*pi/8) - i sin(e*pi/8) (forward); conjugate for the inverse
+  T c, s;
+  if (E == 1) { c = c1; s = s1; }
+  else if (E == 2) { c = h; s = h; }
+  else if (E == 3) { c = s1; s = c1; }
+  else if (E == 6) { c = -h; s = h; }
+  else { c = -c1; s = -s1; }  // E == 9
+  if (INV) s = -s;
+  return C2<T>{v.x * c + v.y * s, v.y * c - v.x * s};
+}
+
+// 16-point DFT, natural order in and out: y_q = sum_r x_r W16^{rq}.  4x4 decomposition:
+// radix-4 over r1 (r = 4 r1 + r0), internal twiddles W16^{r0 q0}, radix-4 over r0 (q = q0 + 4 q1).
+template <bool INV, typename T>
+SSR_HD void bfly16(C2<T>* x) {
+#pragma unroll
+  for (int r0 = 0; r0 < 4; ++r0) bfly4<INV>(x[r0], x[4 + r0], x[8 + r0], x[12 + r0]);
+  // now x[4*q0 + r0] holds u[r0][q0]
+  x[5] = mul_w16<INV, 1>(x[5]);
+  x[6] = mul_w16<INV, 2>(x[6]);
+  x[7] = mul_w16<INV, 3>(x[7]);
+  x[9] = mul_w16<INV, 2>(x[9]);
+  x[10] = mul_mi<INV>(x[10]);
+  x[11] = mul_w16<INV, 6>(x[11]);
+  x[13] = mul_w16<INV, 3>(x[13]);
+  x[14] = mul_w16<INV, 6>(x[14]);
+  x[15] = mul_w16<INV, 9>(x[15]);
+#pragma unroll
+  for (int q0 = 0; q0 < 4; ++q0) bfly4<INV>(x[4 * q0], x[4 * q0 + 1], x[4 * q0 + 2], x[4 * q0 + 3]);
+  // x[4*q0 + q1] holds y[q0 + 4 q1]: transpose the 4x4 index to natural order
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) {
+      C2<T> t = x[4 * a + b];
+      x[4 * a + b] = x[4 * b + a];
+      x[4 * b + a] = t;
+    }
+}
+
 template <int R, bool INV, typename T>
 SSR_HD void bfly(C2<T>* x) {
-  if (R == 8) {
+  if (R == 16) {
+    bfly16<INV>(x);
+  } else if (R == 8) {
     bfly8<INV>(x);
   } else {
     bfly4<INV>(x[0], x[1], x[2], x[3]);

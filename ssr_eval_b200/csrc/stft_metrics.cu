@@ -15,6 +15,7 @@
 // spectra are separated, rounded to complex64 like librosa's store, and every metric formula runs
 // in float32 exactly as torch does on the CPU; cross-frame sums are kept in float64.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -22,6 +23,7 @@
 #include "common.cuh"
 #include "fft_core.cuh"
 #include "stft_tables.hpp"
+#include "k1_map.cuh"
 
 namespace ssr {
 
@@ -32,6 +34,15 @@ std::string& last_error_ref() {
 std::atomic<uint64_t>& launch_counter() {
   static std::atomic<uint64_t> c{0};
   return c;
+}
+
+struct TimingState {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;
+};
+static TimingState& timing() {
+  static TimingState t;
+  return t;
 }
 
 constexpr int kThreads = 256;
@@ -204,7 +215,7 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
         __syncthreads();
       }
       // ---- epilogue over the F = n_fft/2+1 bins
-      float lsd_acc = 0.f, pet = 0.f, ptt = 0.f, pee = 0.f, qet = 0.f, qtt = 0.f, qee = 0.f;
+      float lsd_acc = 0.f;
       float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
       float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
       for (int k = tid; k < F; k += kThreads) {
@@ -230,28 +241,25 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
           float l = log10f(q);
           lsd_acc += l * l;
         }
+        // sispec is evaluated in closed form from three sums (finalize); at 40+ dB the difference
+        // S_ee - S_et^2/S_tt cancels 4+ digits, so the products (exact in float64) are summed in float64.
         if (want_lin) {
-          pet += me * mt;
-          ptt += mt * mt;
-          pee += me * me;
+          const double de = (double)me, dt = (double)mt;
+          s_et = fma(de, dt, s_et);
+          s_tt = fma(dt, dt, s_tt);
+          s_ee = fma(de, de, s_ee);
         }
         if (want_log) {
-          float le = log10f(me + 1e-12f), lt = log10f(mt + 1e-12f);
-          qet += le * lt;
-          qtt += lt * lt;
-          qee += le * le;
+          const double le = (double)log10f(me + 1e-12f), lt = (double)log10f(mt + 1e-12f);
+          l_et = fma(le, lt, l_et);
+          l_tt = fma(lt, lt, l_tt);
+          l_ee = fma(le, le, l_ee);
         }
       }
       if (want_lsd) {
         float w = warp_sum(lsd_acc);
         if (lane == 0) lsd_part[fi][warp] = w;
       }
-      s_et += (double)pet;
-      s_tt += (double)ptt;
-      s_ee += (double)pee;
-      l_et += (double)qet;
-      l_tt += (double)qtt;
-      l_ee += (double)qee;
       __syncthreads();  // buf is rewritten by the next frame's load
     }
 
@@ -274,6 +282,172 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
       double r = 0.0;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) r += red[w][tid];
+      partials[(size_t)item * kPartials + tid] = r;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1, specialised: n_fft = 2048 (BASELINE config 2 and every evaluation at 44.1 kHz).
+// 128 threads, 16 points per thread: radix 16 x 16 x 8 in-place DIF.
+//   pass 1: samples come straight from global memory (coalesced, window folded in), the 15
+//           pass-1 twiddles of a thread never change and live in registers for the CTA's lifetime;
+//   pass 2: twiddles W_128^{jq} (120 values) from a conflict-free shared table;
+//   pass 3: no twiddles; every thread transforms a butterfly AND its Hermitian partner
+//           (k1_map.cuh), so Z[k] and Z[N-k] meet in registers and the epilogue needs no
+//           further shared-memory traffic.
+// Shared-memory traffic per frame: 2 exchanges (4 x 32 KB) + 30 KB of twiddles.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kV2Threads, 3)
+k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __restrict__ tgt,
+                    const long long* __restrict__ offsets, const int* __restrict__ item_start,
+                    const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
+                    double* __restrict__ partials, float* __restrict__ spec_e,
+                    float* __restrict__ spec_t, const long long* __restrict__ spec_off) {
+  constexpr int N = 2048, F = 1025, NW = kV2Threads / 32;
+  __shared__ __align__(16) cd buf[N + N / 8];
+  __shared__ __align__(16) cd tw2[15 * 8];
+  __shared__ float lsd_part[kMaxChunk][NW];
+  __shared__ double red[NW][kPartials];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hop = P.hop;
+  const bool want_lsd = flags & SSR_METRIC_LSD, want_log = flags & SSR_METRIC_LOG_SISPEC,
+             want_lin = flags & SSR_METRIC_SISPEC;
+
+  // per-thread constants
+  cd tw1[15];
+#pragma unroll
+  for (int q = 1; q < 16; ++q) tw1[q - 1] = P.tw[tid * q];
+  if (tid < 120) tw2[tid] = P.tw[16 * (tid & 7) * ((tid >> 3) + 1)];  // tw2[(q-1)*8 + j] = W_128^{jq}
+  int ia, ib;
+  v2_thread_butterflies(tid, &ia, &ib);
+  const bool special = (tid == kV2Threads - 1);
+  const int ka = v2_klow(ia), kb = v2_klow(ib);
+  const int j2 = tid & 7, base2 = (tid >> 3) * 128 + j2;
+  __syncthreads();
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int p = item_pair[item];
+    const int c = item - item_start[p];
+    const long long off = offsets[p];
+    const long long L = offsets[p + 1] - off;
+    const long long T = stft_frames(L, N, hop);
+    const long long f0 = (long long)c * chunk;
+    const int nf = (int)min((long long)chunk, T - f0);
+    const float* xe = est + off;
+    const float* xt = tgt + off;
+    double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
+
+    for (int fi = 0; fi < nf; ++fi) {
+      const long long f = f0 + fi;
+      const long long start = f * hop - N / 2;
+      cd v[16];
+      // ---- pass 1: load + window, radix-16, twiddle, store
+      if (start >= 0 && start + N <= L) {
+        const float* pt = xt + start + tid;
+        const float* pe = xe + start + tid;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const double w = __ldg(P.win_half + tid + 128 * r);
+          v[r] = cd{w * (double)__ldg(pt + 128 * r), w * (double)__ldg(pe + 128 * r)};
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const long long idx = reflect_index(start + tid + 128 * r, L);
+          const double w = __ldg(P.win_half + tid + 128 * r);
+          v[r] = cd{w * (double)__ldg(xt + idx), w * (double)__ldg(xe + idx)};
+        }
+      }
+      bfly16<false>(v);
+      buf[pad_idx(tid)] = v[0];
+#pragma unroll
+      for (int q = 1; q < 16; ++q) buf[pad_idx(tid + 128 * q)] = cmul(v[q], tw1[q - 1]);
+      __syncthreads();
+      // ---- pass 2: sub-transforms of length 128 (stride 8)
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = buf[pad_idx(base2 + 8 * r)];
+      bfly16<false>(v);
+      buf[pad_idx(base2)] = v[0];
+#pragma unroll
+      for (int q = 1; q < 16; ++q) buf[pad_idx(base2 + 8 * q)] = cmul(v[q], tw2[(q - 1) * 8 + j2]);
+      __syncthreads();
+      // ---- pass 3: two radix-8 butterflies (a and its Hermitian partner b), no twiddles
+      cd* a = v;
+      cd* b = v + 8;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        a[r] = buf[pad_idx(8 * ia + r)];
+        b[r] = buf[pad_idx(8 * ib + r)];
+      }
+      __syncthreads();  // buf may now be overwritten by the next frame's pass 1
+      bfly8<false>(a);
+      bfly8<false>(b);
+      // ---- epilogue, from registers
+      float lsd_acc = 0.f;
+      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
+      float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
+      auto emit = [&](int k, cd zk, cd zn) {
+        // T = (Z[k] + conj Z[N-k]) / 2,  E = (Z[k] - conj Z[N-k]) / (2i); the 1/2 is in the window
+        const float tre = (float)(zk.x + zn.x), tim = (float)(zk.y - zn.y);
+        const float ere = (float)(zk.y + zn.y), eim = (float)(zn.x - zk.x);
+        const float mt = sqrtf(tre * tre + tim * tim);
+        const float me = sqrtf(ere * ere + eim * eim);
+        if (st) st[k] = mt;
+        if (se) se[k] = me;
+        if (want_lsd) {
+          const float den = me + 1e-12f;
+          const float l = log10f((mt * mt) / (den * den) + 1e-12f);
+          lsd_acc += l * l;
+        }
+        if (want_lin) {
+          const double de = (double)me, dt = (double)mt;
+          s_et = fma(de, dt, s_et);
+          s_tt = fma(dt, dt, s_tt);
+          s_ee = fma(de, de, s_ee);
+        }
+        if (want_log) {
+          const double le = (double)log10f(me + 1e-12f), lt = (double)log10f(mt + 1e-12f);
+          l_et = fma(le, lt, l_et);
+          l_tt = fma(lt, lt, l_tt);
+          l_ee = fma(le, le, l_ee);
+        }
+      };
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const cd za = special ? a[(8 - q) & 7] : b[7 - q];
+        const cd zb = special ? b[7 - q] : a[7 - q];
+        emit(ka + 256 * q, a[q], za);
+        emit(kb + 256 * q, b[q], zb);
+      }
+      if (special) emit(1024, a[4], a[4]);
+      if (want_lsd) {
+        const float w = warp_sum(lsd_acc);
+        if (lane == 0) lsd_part[fi][warp] = w;
+      }
+    }
+    __syncthreads();
+    // ---- per-item reduction -> partials[item][0..7]
+    double lsd_sum = 0.0;
+    if (want_lsd && tid < nf) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sacc += lsd_part[tid][w];
+      lsd_sum = (double)sqrtf(sacc / (float)F);  // torch.mean(dim=3) ** 0.5 in float32
+    }
+    double vals[7] = {lsd_sum, s_et, s_tt, s_ee, l_et, l_tt, l_ee};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const double r = warp_sum(vals[i]);
+      if (lane == 0) red[warp][i] = r;
+    }
+    __syncthreads();
+    if (tid < 7) {
+      double r = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) r += red[w][tid];
       partials[(size_t)item * kPartials + tid] = r;
     }
     __syncthreads();
@@ -420,6 +594,16 @@ __global__ void k_finalize(const long long* __restrict__ offsets, int n, int n_f
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// SSR_FORCE_GENERIC_K1=1 routes n_fft 2048 through the generic radix-8 kernel (A/B tests only)
+static bool force_generic_k1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_FORCE_GENERIC_K1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 struct WsLayout {
   size_t item_start, item_pair, spec_off, partials, ssim_part, spec_e, spec_t, total;
   int chunk, n_items, tiles_x, tiles_per_pair;
@@ -437,7 +621,7 @@ static int plan_layout(const ssr_stft_plan* plan, const int64_t* offs, int n, un
     if (T > max_T) max_T = T;
   }
   // aim for ~8 work items per resident CTA slot (148 SMs x 2), bounded to [4, kMaxChunk] frames
-  long long want = 148LL * 2 * 8;
+  long long want = 148LL * 3 * 8;
   long long chunk = (total_frames + want - 1) / want;
   if (chunk < 4) chunk = 4;
   if (chunk > kMaxChunk) chunk = kMaxChunk;
@@ -483,9 +667,25 @@ static int launch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStrea
                      const long long* spec_off) {
   auto kern = k_stft_metrics<LOGM, BLUE>;
   SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TimingState& tm = timing();
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  if (tm.on) {
+    if (!tm.pool.empty()) {
+      ev = tm.pool.back();
+      tm.pool.pop_back();
+    } else {
+      SSR_CUDA_TRY(cudaEventCreate(&ev.first));
+      SSR_CUDA_TRY(cudaEventCreate(&ev.second));
+    }
+    SSR_CUDA_TRY(cudaEventRecord(ev.first, st));
+  }
   kern<<<grid, kThreads, smem, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, n_items,
                                      chunk, flags, partials, spec_e, spec_t, spec_off);
   SSR_LAUNCH_CHECK("k_stft_metrics");
+  if (tm.on) {
+    SSR_CUDA_TRY(cudaEventRecord(ev.second, st));
+    tm.pending.push_back(ev);
+  }
   return SSR_OK;
 }
 
@@ -531,6 +731,31 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   if (per_sm > 2) per_sm = 2;
   int grid = sms * per_sm;
   if (grid > w.n_items) grid = w.n_items;
+  if (!plan->bluestein && plan->logM == 11 && !force_generic_k1()) {
+    int g2 = sms * 3;
+    if (g2 > w.n_items) g2 = w.n_items;
+    TimingState& tm = timing();
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (tm.on) {
+      if (!tm.pool.empty()) {
+        ev = tm.pool.back();
+        tm.pool.pop_back();
+      } else {
+        SSR_CUDA_TRY(cudaEventCreate(&ev.first));
+        SSR_CUDA_TRY(cudaEventCreate(&ev.second));
+      }
+      SSR_CUDA_TRY(cudaEventRecord(ev.first, st));
+    }
+    k_stft_metrics_2048<<<g2, kV2Threads, 0, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair,
+                                                   w.n_items, w.chunk, flags, partials, spec_e, spec_t,
+                                                   spec_off);
+    SSR_LAUNCH_CHECK("k_stft_metrics_2048");
+    if (tm.on) {
+      SSR_CUDA_TRY(cudaEventRecord(ev.second, st));
+      tm.pending.push_back(ev);
+    }
+    return SSR_OK;
+  }
   if (plan->bluestein)
     return dispatch_k1<true>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair,
                              w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off);
@@ -547,6 +772,29 @@ extern "C" {
 int ssr_version(void) { return 100; }
 const char* ssr_last_error(void) { return last_error_ref().c_str(); }
 uint64_t ssr_launch_count(void) { return launch_counter().load(); }
+
+int ssr_timing_enable(int on) {
+  timing().on = on != 0;
+  return SSR_OK;
+}
+
+int ssr_timing_collect(double* total_ms, int* n_launches) {
+  TimingState& tm = timing();
+  double tot = 0.0;
+  int n = 0;
+  for (auto& ev : tm.pending) {
+    SSR_CUDA_TRY(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    SSR_CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    tot += ms;
+    ++n;
+    tm.pool.push_back(ev);
+  }
+  tm.pending.clear();
+  if (total_ms) *total_ms = tot;
+  if (n_launches) *n_launches = n;
+  return SSR_OK;
+}
 
 int ssr_stft_plan_create(ssr_stft_plan** out, int n_fft, int hop, const double* window_host) {
   if (!out) return fail(SSR_ERR_INVALID, "plan pointer is NULL");

@@ -1,0 +1,304 @@
+"""Batch engine: ragged utterance batches in HBM -> the sm_100a kernels behind the C ABI.
+
+PyTorch is used for device memory, streams and (in dist.py) torch.distributed only; all arithmetic
+of the hot path happens in libssr_b200.so.  Everything here needs a CUDA device -- no CPU fallback.
+"""
+import ctypes
+from math import gcd
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise N.NativeError("ssr_eval_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def offsets_of(lengths):
+    off = np.zeros(len(lengths) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(lengths, dtype=np.int64), out=off[1:])
+    return off
+
+
+def pack_ragged(arrays, pinned=False):
+    """Concatenate 1-D float arrays into one float32 host buffer + int64 offsets."""
+    off = offsets_of([len(a) for a in arrays])
+    flat = torch.empty(int(off[-1]), dtype=torch.float32, pin_memory=pinned)
+    fn = flat.numpy()
+    for a, s, e in zip(arrays, off[:-1], off[1:]):
+        fn[s:e] = a
+    return flat, off
+
+
+class _Workspace:
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class StftMetrics:
+    """K1+K2: batched STFT -> {lsd, log_sispec, sispec, ssim} (ssr_eval/metrics.py:92-132)."""
+
+    # spectrogram workspace kept around the L2 size so the K1 -> K2 round trip stays on chip
+    SSIM_SUBBATCH_BYTES = 96 << 20
+
+    def __init__(self, n_fft, hop, window=None):
+        _require_cuda()
+        self.n_fft, self.hop = int(n_fft), int(hop)
+        self.n_bins = self.n_fft // 2 + 1
+        self._plan = ctypes.c_void_p()
+        w = None
+        if window is not None:
+            w = np.ascontiguousarray(window, dtype=np.float64)
+            assert w.shape == (self.n_fft,)
+        N.check(N.lib().ssr_stft_plan_create(ctypes.byref(self._plan), self.n_fft, self.hop,
+                                             _np_ptr(w) if w is not None else None), "ssr_stft_plan_create")
+        self._ws = _Workspace()
+
+    def __del__(self):
+        try:
+            if self._plan:
+                N.lib().ssr_stft_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+    def num_frames(self, length):
+        return int(N.lib().ssr_stft_num_frames(self._plan, int(length)))
+
+    def _run(self, est_dev, tgt_dev, off_np, off_dev, out_dev, flags):
+        n = len(off_np) - 1
+        need = N.lib().ssr_stft_metrics_workspace_bytes(self._plan, _np_ptr(off_np), n, flags)
+        if need == 0:
+            raise N.NativeError("workspace query failed: " + (N.lib().ssr_last_error() or b"").decode())
+        ws = self._ws.get(need, est_dev.device)
+        N.check(N.lib().ssr_stft_metrics_batched(self._plan, _ptr(est_dev), _ptr(tgt_dev), _np_ptr(off_np),
+                                                 _ptr(off_dev), n, flags, _ptr(out_dev), _ptr(ws),
+                                                 ws.numel(), _stream()), "ssr_stft_metrics_batched")
+
+    def metrics_device(self, est_dev, tgt_dev, offsets, flags=N.METRIC_ALL, offsets_dev=None, out=None):
+        """est_dev/tgt_dev: flat float32 CUDA tensors (ragged, same offsets). Returns (n,4) float64
+        CUDA tensor [lsd, log_sispec, sispec, ssim] (NaN where not requested). Asynchronous."""
+        off_np = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(off_np) - 1
+        assert est_dev.is_cuda and tgt_dev.is_cuda and est_dev.dtype == torch.float32
+        assert est_dev.numel() >= off_np[-1] and tgt_dev.numel() >= off_np[-1]
+        dev = est_dev.device
+        if offsets_dev is None:
+            offsets_dev = torch.from_numpy(off_np).to(dev)
+        if out is None:
+            out = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        if not (flags & N.METRIC_SSIM):
+            self._run(est_dev, tgt_dev, off_np, offsets_dev, out, flags)
+            return out
+        # SSIM needs both magnitude spectrograms: run sub-batches whose spectrograms fit in L2
+        frames = np.array([self.num_frames(l) for l in np.diff(off_np)], dtype=np.int64)
+        bytes_per = frames * self.n_bins * 8
+        s = 0
+        while s < n:
+            e, acc = s, 0
+            while e < n and (e == s or acc + bytes_per[e] <= self.SSIM_SUBBATCH_BYTES):
+                acc += bytes_per[e]
+                e += 1
+            base = int(off_np[s])
+            sub_off = off_np[s:e + 1] - base
+            sub_off_dev = offsets_dev[s:e + 1] - base if s else offsets_dev[:e + 1]
+            self._run(est_dev[base:], tgt_dev[base:], np.ascontiguousarray(sub_off), sub_off_dev.contiguous(),
+                      out[s:e], flags)
+            s = e
+        return out
+
+    def metrics(self, est_list, tgt_list, flags=N.METRIC_ALL):
+        """Host entry: lists of 1-D float arrays (already truncated to equal length per pair).
+        Returns (n,4) float64 numpy."""
+        assert len(est_list) == len(tgt_list) and len(est_list) > 0
+        for a, b in zip(est_list, tgt_list):
+            assert len(a) == len(b)
+        e_h, off = pack_ragged(est_list, pinned=True)
+        t_h, _ = pack_ragged(tgt_list, pinned=True)
+        e_d = e_h.cuda(non_blocking=True)
+        t_d = t_h.cuda(non_blocking=True)
+        return self.metrics_device(e_d, t_d, off, flags).cpu().numpy()
+
+    def magnitude(self, wav_list):
+        """|STFT| of each utterance: list of (T_i, F) float32 numpy arrays (metrics.py:26-30)."""
+        x_h, off = pack_ragged(wav_list, pinned=True)
+        x_d = x_h.cuda(non_blocking=True)
+        n = len(wav_list)
+        frames = [self.num_frames(len(w)) for w in wav_list]
+        spec = torch.empty(int(sum(frames)) * self.n_bins, dtype=torch.float32, device=x_d.device)
+        off_dev = torch.from_numpy(off).to(x_d.device)
+        need = N.lib().ssr_stft_metrics_workspace_bytes(self._plan, _np_ptr(off), n, 0)
+        ws = self._ws.get(need, x_d.device)
+        N.check(N.lib().ssr_stft_magnitude_batched(self._plan, _ptr(x_d), _np_ptr(off), _ptr(off_dev), n,
+                                                   _ptr(spec), _ptr(ws), ws.numel(), _stream()),
+                "ssr_stft_magnitude_batched")
+        s = spec.cpu().numpy()
+        out, pos = [], 0
+        for T in frames:
+            out.append(s[pos:pos + T * self.n_bins].reshape(T, self.n_bins))
+            pos += T * self.n_bins
+        return out
+
+
+def resample_poly_taps(up, down, dtype=np.float32):
+    """The FIR scipy.signal.resample_poly designs for window=("kaiser", 5.0): firwin cast to the
+    input dtype, then scaled by `up` (scipy/signal/_signaltools.py resample_poly)."""
+    from scipy.signal import firwin
+    max_rate = max(up, down)
+    half_len = 10 * max_rate
+    h = firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0)).astype(dtype)
+    h *= up
+    return h
+
+
+class PolyphaseResampler:
+    """K3: scipy.signal.resample_poly(x, up, down) for float32 batches."""
+
+    def __init__(self, up, down):
+        _require_cuda()
+        g = gcd(int(up), int(down))
+        self.up, self.down = int(up) // g, int(down) // g
+        self.identity = self.up == 1 and self.down == 1
+        self._plan = ctypes.c_void_p()
+        if not self.identity:
+            taps = np.ascontiguousarray(resample_poly_taps(self.up, self.down))
+            N.check(N.lib().ssr_resample_plan_create(ctypes.byref(self._plan), self.up, self.down,
+                                                     _np_ptr(taps), len(taps)), "ssr_resample_plan_create")
+
+    def __del__(self):
+        try:
+            if self._plan:
+                N.lib().ssr_resample_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+    def out_len(self, n_in):
+        t = int(n_in) * self.up
+        return t // self.down + (1 if t % self.down else 0)
+
+    def resample_device(self, x_dev, in_offsets, in_offsets_dev=None):
+        """Returns (y_dev, out_offsets numpy, out_offsets_dev). Asynchronous."""
+        in_off = np.ascontiguousarray(in_offsets, dtype=np.int64)
+        if in_offsets_dev is None:
+            in_offsets_dev = torch.from_numpy(in_off).to(x_dev.device)
+        if self.identity:
+            return x_dev, in_off, in_offsets_dev
+        n = len(in_off) - 1
+        out_off = offsets_of([self.out_len(l) for l in np.diff(in_off)])
+        out_off_dev = torch.from_numpy(out_off).to(x_dev.device)
+        y = torch.empty(int(out_off[-1]), dtype=torch.float32, device=x_dev.device)
+        N.check(N.lib().ssr_resample_poly_batched(self._plan, _ptr(x_dev), _np_ptr(in_off), _ptr(in_offsets_dev),
+                                                  _ptr(y), _np_ptr(out_off), _ptr(out_off_dev), n, _stream()),
+                "ssr_resample_poly_batched")
+        return y, out_off, out_off_dev
+
+    def resample(self, wav_list):
+        x_h, off = pack_ragged(wav_list, pinned=True)
+        y, out_off, _ = self.resample_device(x_h.cuda(non_blocking=True), off)
+        yh = y.cpu().numpy()
+        return [yh[s:e].copy() for s, e in zip(out_off[:-1], out_off[1:])]
+
+
+class HardLowpass:
+    """K4: stft_hard_lowpass_v0 (ssr_eval/lowpass.py:17-28) for float32 batches."""
+
+    def __init__(self, n_fft=2048, hop=441):
+        _require_cuda()
+        self.n_fft, self.hop = int(n_fft), int(hop)
+        self.n_bins = self.n_fft // 2 + 1
+        self._plan = ctypes.c_void_p()
+        N.check(N.lib().ssr_lowpass_plan_create(ctypes.byref(self._plan), self.n_fft, self.hop),
+                "ssr_lowpass_plan_create")
+
+    def __del__(self):
+        try:
+            if self._plan:
+                N.lib().ssr_lowpass_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+    def cut_bin(self, lowpass_ratio):
+        return int(self.n_bins * lowpass_ratio)  # lowpass.py:23
+
+    def apply_device(self, x_dev, offsets, cut_bins, offsets_dev=None):
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        if offsets_dev is None:
+            offsets_dev = torch.from_numpy(off).to(x_dev.device)
+        n = len(off) - 1
+        cb = torch.as_tensor(np.asarray(cut_bins, dtype=np.int32)).to(x_dev.device)
+        assert cb.numel() == n
+        y = torch.empty(int(off[-1]), dtype=torch.float32, device=x_dev.device)
+        N.check(N.lib().ssr_stft_hard_lowpass_batched(self._plan, _ptr(x_dev), _np_ptr(off), _ptr(offsets_dev), n,
+                                                      _ptr(cb), _ptr(y), _stream()),
+                "ssr_stft_hard_lowpass_batched")
+        return y
+
+    def apply(self, wav_list, lowpass_ratios):
+        x_h, off = pack_ragged(wav_list, pinned=True)
+        cuts = [self.cut_bin(r) for r in lowpass_ratios]
+        y = self.apply_device(x_h.cuda(non_blocking=True), off, cuts).cpu().numpy()
+        return [y[s:e].copy() for s, e in zip(off[:-1], off[1:])]
+
+
+class HostPipeline:
+    """Host-buffer entry point of K1/K2: (pinned) host batches are streamed to the GPU in chunks on a
+    copy stream, double-buffered against the kernels, and the (n, 4) float64 result is read back.
+    This is the path timed as ``e2e`` in bench.py."""
+
+    def __init__(self, engine, max_pairs, max_len, chunk_pairs=64):
+        _require_cuda()
+        self.engine = engine
+        self.chunk_samples = int(min(max_pairs, chunk_pairs)) * int(max_len)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.slots = [(torch.empty(self.chunk_samples, dtype=torch.float32, device=dev),
+                       torch.empty(self.chunk_samples, dtype=torch.float32, device=dev)) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+
+    def run(self, est_host, tgt_host, offsets, flags=N.METRIC_ALL):
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(off) - 1
+        dev = self.slots[0][0].device
+        out = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        compute = torch.cuda.current_stream()
+        s, c = 0, 0
+        while s < n:
+            e = s + 1
+            while e < n and off[e + 1] - off[s] <= self.chunk_samples:
+                e += 1
+            a, b = int(off[s]), int(off[e])
+            if b - a > self.chunk_samples:
+                raise ValueError("utterance longer than the pipeline slot")
+            slot = c % 2
+            se, st = self.slots[slot]
+            with torch.cuda.stream(self.copy_stream):
+                if c >= 2:
+                    self.copy_stream.wait_event(self.free[slot])
+                se[:b - a].copy_(est_host[a:b], non_blocking=True)
+                st[:b - a].copy_(tgt_host[a:b], non_blocking=True)
+                self.ready[slot].record(self.copy_stream)
+            compute.wait_event(self.ready[slot])
+            self.engine.metrics_device(se, st, off[s:e + 1] - a, flags, out=out[s:e])
+            self.free[slot].record(compute)
+            s, c = e, c + 1
+        return out.cpu().numpy()

@@ -1,0 +1,250 @@
+"""``SSR_Eval_Helper`` / ``BasicTestee`` with the reference's interface (ssr_eval/eval.py), rebuilt
+as batch -> GPU: all files of a speaker are degraded in one K4/K3 launch, pushed through the user's
+``infer`` on the host (plugin contract unchanged), resampled in one K3 launch and scored in one
+K1/K2 launch sequence.  Results / JSON schema are the reference's (eval.py:175-227).
+
+Out of scope here (external binaries / network): the VCTK download
+(eval.py:102-119), sox (eval.py:133) and mp3 encoding (eval.py:302-325).
+"""
+import os
+from datetime import datetime
+
+import numpy as np
+
+from . import _native as N
+from .audio_io import load_audio, write_wav
+from .engine import PolyphaseResampler
+from .lowpass import lowpass, stft_hard_lowpass_batch
+from .metrics import AudioMetrics
+from .utils import dict_mean, write_json
+
+
+class BasicTestee:
+    """Plugin base class (ssr_eval/eval.py:17-52): subclass and override ``infer``."""
+
+    def __init__(self) -> None:
+        pass
+
+    def _find_cutoff(self, x, threshold=0.95):
+        """Last index where the cumulative energy is below threshold*total (eval.py:21-26)."""
+        level = x[-1] * threshold
+        for i in range(1, x.shape[0]):
+            if x[-i] < level:
+                return x.shape[0] - i
+        return 0
+
+    def _get_cutoff_index(self, x):
+        raise NotImplementedError(
+            "BasicTestee.postprocessing (STFT splice, eval.py:28-41) is a 'next' row of the hot-path "
+            "scope (SURVEY.md section 8f rank 1) and is not built yet")
+
+    def postprocessing(self, x, out):
+        return self._get_cutoff_index(x)
+
+    def tensor2numpy(self, tensor):
+        return tensor.detach().cpu().numpy()
+
+    def infer(self, x):
+        """x: [samples] at input_sr -> [samples] at output_sr (or (wav, extra_metrics_dict))."""
+        return x
+
+
+class SSR_Eval_Helper:
+    def __init__(self, testee, input_sr, output_sr, evaluation_sr=44100, test_name="test",
+                 test_data_root="./datasets/vctk_test", setting_lowpass_filtering=None,
+                 setting_subsampling=None, setting_fft=None, setting_mp3_compression=None,
+                 save_processed_result=False):
+        self.testee = testee
+        self.test_name = test_name
+        self.test_data_root = test_data_root
+        self.save_processed_result = save_processed_result
+        # eval.py:121-126: cutoffs are doubled IN PLACE in the caller's dict (keys are named by 2*cutoff)
+        self.setting_lowpass_filtering = self._cutoff2sr(setting_lowpass_filtering)
+        self.setting_fft = self._cutoff2sr(setting_fft)
+        self.setting_subsampling = self._cutoff2sr(setting_subsampling)
+        self.setting_mp3_compression = setting_mp3_compression
+        self.model_input_sr = input_sr
+        self.model_output_sr = output_sr
+        self.evaluationset_sr = evaluation_sr
+        assert self.evaluationset_sr <= 48000, \
+            "Our evaluation set only support up to 48 kHz target sampling rate"
+        self.audio_metrics = AudioMetrics(self.evaluationset_sr)
+        self._out_resampler = None
+        if not os.path.isdir(test_data_root):
+            raise FileNotFoundError(
+                "test_data_root %r does not exist; the reference would download VCTK here "
+                "(eval.py:102-119) -- there is no network, place the test set there" % test_data_root)
+
+    def _cutoff2sr(self, dic):
+        if dic is None:
+            return None
+        dic["cutoff_freq"] = [x * 2 for x in dic["cutoff_freq"]]
+        return dic
+
+    # ------------------------------------------------------------------ degradation (eval.py:229-270)
+    def _degrade_batch(self, xs, sr):
+        """xs: list of float32 waveforms at `sr` -> list of {key: waveform} (one dict per file)."""
+        outs = [dict() for _ in xs]
+        lp = self.setting_lowpass_filtering
+        if lp is not None:
+            table = (("butter", "bw", "butter"), ("cheby", "ch", "cheby1"),
+                     ("ellip", "el", "ellip"), ("bessel", "bessel", "bessel"))
+            for needle, tag, ftype in table:
+                if needle not in lp["filter"]:
+                    continue
+                for low_rate in lp["cutoff_freq"]:
+                    for order in lp["filter_order"]:
+                        if low_rate == sr:
+                            low_rate -= 1
+                        key = "proc_%s_%s_%s_%s" % (tag, low_rate, order, sr)
+                        for x, o in zip(xs, outs):
+                            o[key] = lowpass(x, low_rate // 2, sr, order=order, _type=ftype)
+                            assert o[key].shape == x.shape, str((o[key].shape, x.shape))
+        if self.setting_subsampling is not None:
+            for low_rate in self.setting_subsampling["cutoff_freq"]:
+                if low_rate == sr:
+                    low_rate -= 1
+                key = "proc_subsampling_%s_%s" % (low_rate, sr)
+                for x, o in zip(xs, outs):
+                    o[key] = lowpass(x, low_rate // 2, sr, order=1, _type="subsampling")
+        if self.setting_mp3_compression is not None:
+            raise NotImplementedError("mp3 degradation needs the external sox binary (eval.py:302-325); out of scope")
+        if self.setting_fft is not None:
+            keys, ratios = [], []
+            for low_rate in self.setting_fft["cutoff_freq"]:
+                if low_rate == sr:
+                    low_rate -= 1
+                keys.append("proc_fft_%s_%s" % (low_rate, sr))
+                # lowpass(x, low_rate // 2, sr, _type="stft_hard") -> ratio = highcut / int(fs / 2)
+                ratios.append((low_rate // 2) / int(sr / 2))
+            waves = [x for x in xs for _ in keys]
+            rr = [r for _ in xs for r in ratios]
+            ys = stft_hard_lowpass_batch(waves, rr)
+            for i, o in enumerate(outs):
+                for j, key in enumerate(keys):
+                    o[key] = ys[i * len(keys) + j]
+        return outs
+
+    def preprocess(self, file, sr):
+        x, _ = load_audio(file, sr=sr)
+        return self._degrade_batch([x], sr)[0]
+
+    # ------------------------------------------------------------------ scoring (eval.py:128-156)
+    def _resample_to_eval(self, waves):
+        if self.model_output_sr == self.evaluationset_sr:
+            return waves
+        if self._out_resampler is None:
+            self._out_resampler = PolyphaseResampler(self.evaluationset_sr, self.model_output_sr)
+        ys = self._out_resampler.resample([np.asarray(w, dtype=np.float32) for w in waves])
+        out = []
+        ratio = float(self.evaluationset_sr) / self.model_output_sr
+        for w, y in zip(waves, ys):
+            n = int(np.ceil(len(w) * ratio))  # librosa.resample: fix_length to ceil(L*ratio)
+            out.append(y[:n] if len(y) >= n else np.pad(y, (0, n - len(y))))
+        return out
+
+    def evaluate_batch(self, files):
+        """{file: {key: {metric: float}}} for a list of audio paths -- one launch sequence."""
+        xs = [load_audio(f, sr=self.model_input_sr)[0] for f in files]
+        targets = [load_audio(f, sr=self.evaluationset_sr)[0] for f in files]
+        degraded = self._degrade_batch(xs, self.model_input_sr)
+        items, processed, extras = [], [], []
+        for fi, d in enumerate(degraded):
+            for k, v in d.items():
+                ret = self.testee.infer(v)
+                extra = {}
+                if type(ret) == tuple:
+                    ret, extra = ret
+                items.append((fi, k))
+                processed.append(np.asarray(ret))
+                extras.append(extra)
+        processed = self._resample_to_eval(processed)
+        scores = self.audio_metrics.evaluation_batch(processed, [targets[fi] for fi, _ in items])
+        result = {f: {} for f in files}
+        for (fi, k), s, extra, wav in zip(items, scores, extras, processed):
+            s.update(extra)
+            result[files[fi]][k] = s
+            if self.save_processed_result:
+                write_wav(files[fi] + k + "_processed_" + self.test_name + ".wav", wav, self.evaluationset_sr)
+        return result
+
+    def evaluate_single(self, file):
+        return self.evaluate_batch([file])[file]
+
+    def get_test_file_list(self, path):
+        """eval.py:158-169 (skips processed outputs written next to the inputs)."""
+        ret = []
+        for file in os.listdir(path):
+            if file[-4:] != ".wav" and file[-5:] != ".flac":
+                continue
+            if "DS_Store" in file or "proc" in file:
+                continue
+            ret.append(file)
+        return ret
+
+    def _speakers(self, limit_test_speaker):
+        out = []
+        for speaker in sorted(os.listdir(self.test_data_root)):
+            if not os.path.isdir(os.path.join(self.test_data_root, speaker)):
+                continue
+            if "p" not in speaker and "s" not in speaker:
+                continue
+            if limit_test_speaker > 0 and len(out) >= limit_test_speaker:
+                break
+            out.append(speaker)
+        return out
+
+    def evaluate(self, limit_test_nums=-1, limit_test_speaker=-1, batch_files=64, shard=None):
+        """eval.py:171-227.  ``shard=(rank, world)`` evaluates files i % world == rank and merges the
+        per-speaker tables with one all-reduce (see dist.py); default: torch.distributed state."""
+        from . import dist
+        rank, world = dist.rank_world() if shard is None else shard
+        final_result, work = {}, []
+        for speaker in self._speakers(limit_test_speaker):
+            print("Speaker:", speaker)
+            final_result[speaker] = {}
+            files = sorted(self.get_test_file_list(os.path.join(self.test_data_root, speaker)))
+            assert len(files) != 0, os.path.join(self.test_data_root, speaker)
+            if limit_test_nums > 0:
+                files = files[:limit_test_nums]
+            work += [(speaker, f) for f in files]
+        mine = work[rank::world]
+        local = {}
+        for s in range(0, len(mine), batch_files):
+            chunk = mine[s:s + batch_files]
+            paths = [os.path.join(self.test_data_root, sp, f) for sp, f in chunk]
+            res = self.evaluate_batch(paths)
+            for (sp, f), p in zip(chunk, paths):
+                local[(sp, f)] = res[p]
+        merged = dist.gather_results(local, world)
+        for sp, f in work:
+            final_result[sp][f] = merged[(sp, f)]
+        # aggregation exactly as eval.py:200-216: mean over files per speaker, then mean of speaker means
+        result_cache, averaged_result, distortion_type = {}, {}, []
+        for speaker in final_result.keys():
+            result_cache[speaker] = {}
+            for file in final_result[speaker].keys():
+                distortion_type = list(final_result[speaker][file].keys())
+                break
+            for distortion in distortion_type:
+                result_cache[speaker][distortion] = dict_mean(
+                    [v[distortion] for v in final_result[speaker].values()])
+        speakers = list(final_result.keys())
+        for distortion in distortion_type:
+            averaged_result[distortion] = dict_mean([result_cache[sp][distortion] for sp in speakers])
+        final_result["each_speaker"] = result_cache
+        final_result["averaged"] = averaged_result
+        if rank == 0:
+            os.makedirs("results", exist_ok=True)
+            now = datetime.now()
+            save_path = str(now.date()) + "-" + str(now.time()) + "-" + self.test_name + ".json"
+            write_json(_jsonable(final_result), os.path.join("results", save_path))
+        return final_result
+
+
+def _jsonable(o):
+    if isinstance(o, dict):
+        return {k: _jsonable(v) for k, v in o.items()}
+    if isinstance(o, (np.floating, np.integer)):
+        return o.item()
+    return o

@@ -1,0 +1,127 @@
+"""Low-resolution simulation with the reference's interface (ssr_eval/lowpass.py).
+
+``stft_hard`` (K4) and ``subsampling`` (K3 twice) run on the GPU kernels; the IIR zero-phase filters
+(butter / cheby1 / ellip / bessel via sosfiltfilt) are out of the hot-path scope (SURVEY.md section 2
+row 3, section 8f row 3) and stay a scipy passthrough so the API is complete."""
+import numpy as np
+from scipy.signal import butter, cheby1, cheby2, ellip, bessel, sosfiltfilt
+
+from .engine import HardLowpass, PolyphaseResampler
+
+_hard = {}
+_resamplers = {}
+
+
+def _hard_lowpass(n_fft=2048, hop=441):
+    key = (n_fft, hop)
+    if key not in _hard:
+        _hard[key] = HardLowpass(n_fft, hop)  # FDomainHelper defaults, ssr_eval/dsp.py:9-10
+    return _hard[key]
+
+
+def _resampler(up, down):
+    key = (up, down)
+    if key not in _resamplers:
+        _resamplers[key] = PolyphaseResampler(up, down)
+    return _resamplers[key]
+
+
+def stft_hard_lowpass_v0(data, lowpass_ratio):
+    """ssr_eval/lowpass.py:17-28 -> float32 numpy of the input length."""
+    x = np.asarray(data, dtype=np.float32)
+    return _hard_lowpass().apply([x], [lowpass_ratio])[0]
+
+
+def stft_hard_lowpass_batch(waves, lowpass_ratios):
+    """Batched form: one kernel launch for all (utterance, ratio) pairs."""
+    return _hard_lowpass().apply([np.asarray(w, dtype=np.float32) for w in waves], lowpass_ratios)
+
+
+def align_length(x, y):
+    """Zero-pad or cut ``y`` to len(x) (ssr_eval/lowpass.py:31-51)."""
+    Lx, Ly = len(x), len(y)
+    if Lx == Ly:
+        return y
+    if Lx > Ly:
+        return np.pad(y, (0, Lx - Ly), mode="constant")
+    return y[:Lx]
+
+
+def subsampling(data, lowpass_ratio, fs_ori=44100):
+    """Down- then up-sample by polyphase filtering (ssr_eval/lowpass.py:134-144; fs_ori stays
+    44100 whatever the true rate is, as in the reference)."""
+    fs_down = int(lowpass_ratio * fs_ori)
+    x = np.asarray(data, dtype=np.float32)
+    y = _resampler(fs_down, fs_ori).resample([x])[0]
+    y = _resampler(fs_ori, fs_down).resample([y])[0]
+    if len(y) != len(data):
+        y = align_length(data, y)
+    return y
+
+
+def _design(order, band, btype, ftype):
+    if ftype == "butter":
+        return butter(order, band, btype=btype, output="sos")
+    if ftype == "cheby1":
+        return cheby1(order, 0.1, band, btype=btype, output="sos")
+    if ftype == "cheby2":
+        return cheby2(order, 60, band, btype=btype, output="sos")
+    if ftype == "ellip":
+        return ellip(order, 0.1, 60, band, btype=btype, output="sos")
+    if ftype == "bessel":
+        return bessel(order, band, btype=btype, output="sos")
+    raise Exception(f"The {btype}pass filter {ftype} is not supported!")
+
+
+def lowpass_filter(x, highcut, fs, order, ftype):
+    """Zero-phase IIR low-pass (ssr_eval/lowpass.py:94-131) -- scipy passthrough."""
+    sos = _design(order, highcut / (0.5 * fs), "low", ftype)
+    y = sosfiltfilt(sos, x)
+    return align_length(x, y) if len(y) != len(x) else y
+
+
+def bandpass_filter(x, lowcut, highcut, fs, order, ftype):
+    """Zero-phase IIR band-pass (ssr_eval/lowpass.py:54-91) -- scipy passthrough."""
+    nyq = 0.5 * fs
+    sos = _design(order, [lowcut / nyq, highcut / nyq], "band", ftype)
+    y = sosfiltfilt(sos, x)
+    return align_length(x, y) if len(y) != len(x) else y
+
+
+def limit(integer, high, low):
+    """ssr_eval/lowpass.py:147-153."""
+    if integer > high:
+        return high
+    if integer < low:
+        return low
+    return int(integer)
+
+
+def _check_1d(data):
+    if len(list(data.shape)) != 1:
+        raise ValueError("Error (chebyshev_lowpass_filter): Data " + str(data.shape)
+                         + " should be type 1d time array, (samples,) , can not be (samples, 1)")
+
+
+def lowpass(data, highcut, fs, order=5, _type="butter"):
+    """Dispatcher with the reference's substring matching on ``_type`` (ssr_eval/lowpass.py:156-196)."""
+    order = limit(order, high=10, low=2)
+    _check_1d(data)
+    for name in ("butter", "cheby1", "ellip", "bessel"):
+        if _type in name:
+            return lowpass_filter(x=data, highcut=int(highcut), fs=fs, order=order, ftype=name)
+    if _type in "subsampling":
+        return subsampling(data, lowpass_ratio=highcut / int(fs / 2))
+    if _type in "stft_hard":
+        return stft_hard_lowpass_v0(data, lowpass_ratio=highcut / int(fs / 2))
+    raise ValueError("Error: Unexpected filter type " + _type)
+
+
+def bandpass(data, lowcut, highcut, fs, order=5, _type="butter"):
+    """ssr_eval/lowpass.py:199-256."""
+    _check_1d(data)
+    for name in ("butter", "cheby1", "ellip", "bessel"):
+        if _type in name:
+            return bandpass_filter(x=data, lowcut=int(lowcut), highcut=int(highcut), fs=fs,
+                                   order=limit(order, high=10, low=2), ftype=name)
+    raise ValueError("Error: Unexpected filter type " + _type)

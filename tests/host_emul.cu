@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../ssr_eval_b200/csrc/stft_tables.hpp"
+#include "../ssr_eval_b200/csrc/k1_map.cuh"
 
 using namespace ssr;
 
@@ -136,8 +137,66 @@ static int check_frame(int n_fft) {
   return (errT < 1e-11 * (1 + magT) && errE < 1e-11 * (1 + magT)) ? 0 : 1;
 }
 
+// specialised 2048-point path: radix 16 x 16 x 8 DIF with the register-pairing map of k1_map.cuh
+static int check_v2() {
+  const int N = 2048;
+  std::vector<cd> tw(N), buf(padded_size(N)), x(N);
+  for (int n = 0; n < N; ++n) {
+    long double a = -2 * kPiL * n / N;
+    tw[n] = cd{(double)cosl(a), (double)sinl(a)};
+    x[n] = cd{frand(), frand()};
+    buf[pad_idx(n)] = x[n];
+  }
+  for (int tid = 0; tid < 128; ++tid) dif_pass<16>(buf.data(), N, 2048, tw.data(), tid, 128);
+  for (int tid = 0; tid < 128; ++tid) dif_pass<16>(buf.data(), N, 128, tw.data(), tid, 128);
+  std::vector<long double> Xr(N), Xi(N);
+  for (int k = 0; k < N; ++k) {
+    long double re = 0, im = 0;
+    for (int n = 0; n < N; ++n) {
+      long double a = -2 * kPiL * ((long long)n * k % N) / N;
+      re += x[n].x * cosl(a) - x[n].y * sinl(a);
+      im += x[n].x * sinl(a) + x[n].y * cosl(a);
+    }
+    Xr[k] = re;
+    Xi[k] = im;
+  }
+  std::vector<int> seen(N / 2 + 1, 0);
+  double maxerr = 0;
+  int bad = 0;
+  auto emit = [&](int k, cd zk, cd znk) {
+    if (k < 0 || k > N / 2) { ++bad; return; }
+    seen[k]++;
+    int nk = (N - k) % N;
+    maxerr = fmax(maxerr, fmax(fabs(zk.x - (double)Xr[k]), fabs(zk.y - (double)Xi[k])));
+    maxerr = fmax(maxerr, fmax(fabs(znk.x - (double)Xr[nk]), fabs(znk.y - (double)Xi[nk])));
+  };
+  for (int t = 0; t < 128; ++t) {
+    int ia, ib;
+    v2_thread_butterflies(t, &ia, &ib);
+    cd a[8], b[8];
+    for (int r = 0; r < 8; ++r) {
+      a[r] = buf[pad_idx(8 * ia + r)];
+      b[r] = buf[pad_idx(8 * ib + r)];
+    }
+    bfly8<false>(a);
+    bfly8<false>(b);
+    const bool special = (t == 127);
+    const int ka = v2_klow(ia), kb = v2_klow(ib);
+    for (int q = 0; q < 4; ++q) {
+      emit(ka + 256 * q, a[q], special ? a[(8 - q) & 7] : b[7 - q]);
+      emit(kb + 256 * q, b[q], special ? b[7 - q] : a[7 - q]);
+    }
+    if (special) emit(1024, a[4], a[4]);
+  }
+  for (int k = 0; k <= N / 2; ++k)
+    if (seen[k] != 1) ++bad;
+  printf("v2 (16x16x8) map: bins covered once: %s, maxerr %.3e\n", bad ? "NO" : "yes", maxerr);
+  return (bad == 0 && maxerr < 1e-10) ? 0 : 1;
+}
+
 int main() {
   int bad = 0;
+  bad += check_v2();
   bad += check_fft<8>();
   bad += check_fft<9>();
   bad += check_fft<10>();
