@@ -133,6 +133,12 @@ __global__ void k_setup(const long long* __restrict__ offsets, int n, int n_fft,
   }
 }
 
+__device__ __forceinline__ float __fsqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct SyncThreads {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
@@ -299,6 +305,9 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
 //           further shared-memory traffic.
 // Shared-memory traffic per frame: 2 exchanges (4 x 32 KB) + 30 KB of twiddles.
 // ---------------------------------------------------------------------------------------------
+// FIXED >= 0: the metric flags are the compile-time constant FIXED and no spectrogram is stored
+// (hot configurations: 1 = LSD only, 7 = LSD + log-sispec + sispec); FIXED < 0: run-time flags.
+template <int FIXED>
 __global__ void __launch_bounds__(kV2Threads, 3)
 k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __restrict__ tgt,
                     const long long* __restrict__ offsets, const int* __restrict__ item_start,
@@ -313,8 +322,13 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hop = P.hop;
+  if (FIXED >= 0) flags = (unsigned)FIXED;
   const bool want_lsd = flags & SSR_METRIC_LSD, want_log = flags & SSR_METRIC_LOG_SISPEC,
              want_lin = flags & SSR_METRIC_SISPEC;
+  if (FIXED >= 0) {
+    spec_e = nullptr;
+    spec_t = nullptr;
+  }
 
   // per-thread constants
   cd tw1[15];
@@ -325,7 +339,13 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
   v2_thread_butterflies(tid, &ia, &ib);
   const bool special = (tid == kV2Threads - 1);
   const int ka = v2_klow(ia), kb = v2_klow(ib);
-  const int j2 = tid & 7, base2 = (tid >> 3) * 128 + j2;
+  const int j2 = tid & 7;
+  // padded slots: pass 1 element q -> p1 + 144 q; pass 2 element r -> p2 + 9 r; pass 3 -> 9 i + r
+  cd* const b1 = buf + pad_idx(tid);
+  cd* const b2 = buf + pad_idx((tid >> 3) * 128 + j2);
+  const cd* const b3a = buf + 9 * ia;
+  const cd* const b3b = buf + 9 * ib;
+  const cd* const t2 = tw2 + j2;
   __syncthreads();
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -362,25 +382,25 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
         }
       }
       bfly16<false>(v);
-      buf[pad_idx(tid)] = v[0];
+      b1[0] = v[0];
 #pragma unroll
-      for (int q = 1; q < 16; ++q) buf[pad_idx(tid + 128 * q)] = cmul(v[q], tw1[q - 1]);
+      for (int q = 1; q < 16; ++q) b1[144 * q] = cmul(v[q], tw1[q - 1]);
       __syncthreads();
       // ---- pass 2: sub-transforms of length 128 (stride 8)
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = buf[pad_idx(base2 + 8 * r)];
+      for (int r = 0; r < 16; ++r) v[r] = b2[9 * r];
       bfly16<false>(v);
-      buf[pad_idx(base2)] = v[0];
+      b2[0] = v[0];
 #pragma unroll
-      for (int q = 1; q < 16; ++q) buf[pad_idx(base2 + 8 * q)] = cmul(v[q], tw2[(q - 1) * 8 + j2]);
+      for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
       __syncthreads();
       // ---- pass 3: two radix-8 butterflies (a and its Hermitian partner b), no twiddles
       cd* a = v;
       cd* b = v + 8;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        a[r] = buf[pad_idx(8 * ia + r)];
-        b[r] = buf[pad_idx(8 * ib + r)];
+        a[r] = b3a[r];
+        b[r] = b3b[r];
       }
       __syncthreads();  // buf may now be overwritten by the next frame's pass 1
       bfly8<false>(a);
@@ -390,16 +410,30 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
       float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
       auto emit = [&](int k, cd zk, cd zn) {
-        // T = (Z[k] + conj Z[N-k]) / 2,  E = (Z[k] - conj Z[N-k]) / (2i); the 1/2 is in the window
+        // T = (Z[k] + conj Z[N-k]) / 2,  E = (Z[k] - conj Z[N-k]) / (2i); the 1/2 is in the window.
+        // complex64 rounding as librosa stores it, then float32 arithmetic as torch runs it; the
+        // special functions are the hardware approximations (MUFU sqrt / rcp / lg2, <= 2 ulp), well
+        // inside the differences that already exist between numpy's hypotf / torch's log10 and any
+        // other libm (SSR_EXACT_F32_EPILOGUE switches to the IEEE-rounded forms for A/B tests).
         const float tre = (float)(zk.x + zn.x), tim = (float)(zk.y - zn.y);
         const float ere = (float)(zk.y + zn.y), eim = (float)(zn.x - zk.x);
-        const float mt = sqrtf(tre * tre + tim * tim);
-        const float me = sqrtf(ere * ere + eim * eim);
+        const float tx = tre * tre + tim * tim;  // |T|^2
+        const float ey = ere * ere + eim * eim;  // |E|^2
+#ifdef SSR_EXACT_F32_EPILOGUE
+        const float mt = sqrtf(tx), me = sqrtf(ey);
+#else
+        const float me = __fsqrt_approx(ey);
+        const float mt = (st || want_lin || want_log) ? __fsqrt_approx(tx) : 0.f;
+#endif
         if (st) st[k] = mt;
         if (se) se[k] = me;
         if (want_lsd) {
           const float den = me + 1e-12f;
+#ifdef SSR_EXACT_F32_EPILOGUE
           const float l = log10f((mt * mt) / (den * den) + 1e-12f);
+#else
+          const float l = __log10f(__fdividef(tx, den * den) + 1e-12f);
+#endif
           lsd_acc += l * l;
         }
         if (want_lin) {
@@ -409,7 +443,11 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
           s_ee = fma(de, de, s_ee);
         }
         if (want_log) {
+#ifdef SSR_EXACT_F32_EPILOGUE
           const double le = (double)log10f(me + 1e-12f), lt = (double)log10f(mt + 1e-12f);
+#else
+          const double le = (double)__log10f(me + 1e-12f), lt = (double)__log10f(mt + 1e-12f);
+#endif
           l_et = fma(le, lt, l_et);
           l_tt = fma(lt, lt, l_tt);
           l_ee = fma(le, le, l_ee);
@@ -746,9 +784,19 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
       }
       SSR_CUDA_TRY(cudaEventRecord(ev.first, st));
     }
-    k_stft_metrics_2048<<<g2, kV2Threads, 0, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair,
-                                                   w.n_items, w.chunk, flags, partials, spec_e, spec_t,
-                                                   spec_off);
+    const unsigned m3 = flags & 7u;
+    if (!spec_e && !spec_t && m3 == 1u)
+      k_stft_metrics_2048<1><<<g2, kV2Threads, 0, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair,
+                                                        w.n_items, w.chunk, flags, partials, spec_e,
+                                                        spec_t, spec_off);
+    else if (!spec_e && !spec_t && m3 == 7u)
+      k_stft_metrics_2048<7><<<g2, kV2Threads, 0, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair,
+                                                        w.n_items, w.chunk, flags, partials, spec_e,
+                                                        spec_t, spec_off);
+    else
+      k_stft_metrics_2048<-1><<<g2, kV2Threads, 0, st>>>(plan->dev, est, tgt, offs_dev, item_start,
+                                                         item_pair, w.n_items, w.chunk, flags, partials,
+                                                         spec_e, spec_t, spec_off);
     SSR_LAUNCH_CHECK("k_stft_metrics_2048");
     if (tm.on) {
       SSR_CUDA_TRY(cudaEventRecord(ev.second, st));
