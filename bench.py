@@ -127,12 +127,19 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -158,20 +165,28 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        from datetime import datetime
+        parsed = []
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                ts = datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                parsed.append((ts, float(f[1]), float(f[2]), f[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
+        # samples taken inside the timed regions (device-resident + e2e); 0.15 s slack for the 100 ms period
+        inside = [p for p in parsed if self.t0 is not None and self.t0 - 0.15 <= p[0] <= (self.t1 or 1e30) + 0.15]
+        use = inside if inside else parsed
+        for _, a, b, flags in use:
+            sm.append(a)
+            mx.append(b)
+            for name, v in zip(names, flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_total": len(parsed), "reasons": sorted(reasons)}
 
 
 def make_gpu_batch(n_pairs, device, rank):
@@ -231,13 +246,14 @@ def run_gpu(args):
             td.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     # ---- device-resident timing: exactly K steps, CUDA events on the launching stream
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     N.timing_enable(True)
     N.timing_collect()
     launches0 = N.launch_count()
@@ -252,7 +268,6 @@ def run_gpu(args):
     launches = N.launch_count() - launches0
     k1_ms, k1_n = N.timing_collect()
     N.timing_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -277,6 +292,8 @@ def run_gpu(args):
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
     e2e_value = world * n_pairs * e2e_steps / float(t.item())
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     assert abs(float(np.mean(res[:, 0])) - lsd_mean) < 1e-9
 
     if rank == 0:
@@ -296,7 +313,8 @@ def run_gpu(args):
         traffic_file = os.path.join(ROOT, "profiles", "k1_traffic_bytes.json")
         if os.path.exists(traffic_file):
             try:
-                roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+                # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, scaled per pair
+                roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_pair"] * n_pairs
             except Exception:
                 pass
         cpu = None

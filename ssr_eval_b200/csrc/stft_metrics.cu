@@ -139,6 +139,24 @@ __device__ __forceinline__ float __fsqrt_approx(float x) {
   return r;
 }
 
+// exact float32 -> float64 for normal inputs with four ALU-pipe integer ops (no XU F2F):
+// hi = ((bits asr 3) & 0x8FFFFFFF) + 0x38000000, lo = bits << 29.  Zero / denormal inputs map to
+// +-2^-127-scale values instead of themselves, 26 orders of magnitude below the 1e-12 floors of the
+// metric formulas.
+__device__ __forceinline__ double f2d_bits(float x) {
+  const int b = __float_as_int(x);
+  const int hi = ((b >> 3) & (int)0x8FFFFFFF) + 0x38000000;
+  const int lo = b << 29;
+  return __hiloint2double(hi, lo);
+}
+template <int VAR>
+__device__ __forceinline__ double f2d(float x) {
+  return (VAR & 1) ? f2d_bits(x) : (double)x;
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 struct SyncThreads {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
@@ -307,15 +325,19 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
 // ---------------------------------------------------------------------------------------------
 // FIXED >= 0: the metric flags are the compile-time constant FIXED and no spectrogram is stored
 // (hot configurations: 1 = LSD only, 7 = LSD + log-sispec + sispec); FIXED < 0: run-time flags.
-template <int FIXED>
-__global__ void __launch_bounds__(kV2Threads, 3)
+// VAR: experimental variants (bit 0: float->double input conversion with integer ops on the ALU
+// pipe instead of F2F on the XU pipe; bit 1: L1 prefetch of the next frame's new samples).
+template <int FIXED, int MINB, int VAR>
+__global__ void __launch_bounds__(kV2Threads, MINB)
 k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __restrict__ tgt,
                     const long long* __restrict__ offsets, const int* __restrict__ item_start,
                     const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
                     double* __restrict__ partials, float* __restrict__ spec_e,
                     float* __restrict__ spec_t, const long long* __restrict__ spec_off) {
   constexpr int N = 2048, F = 1025, NW = kV2Threads / 32;
-  __shared__ __align__(16) cd buf[N + N / 8];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* const buf = reinterpret_cast<cd*>(smem_raw);                                // N + N/8 slots
+  float2* const edge_raw = reinterpret_cast<float2*>(smem_raw + sizeof(cd) * (N + N / 8));  // N pairs
   __shared__ __align__(16) cd tw2[15 * 8];
   __shared__ float lsd_part[kMaxChunk][NW];
   __shared__ double red[NW][kPartials];
@@ -371,20 +393,37 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const double w = __ldg(P.win_half + tid + 128 * r);
-          v[r] = cd{w * (double)__ldg(pt + 128 * r), w * (double)__ldg(pe + 128 * r)};
+          v[r] = cd{w * f2d<VAR>(__ldg(pt + 128 * r)), w * f2d<VAR>(__ldg(pe + 128 * r))};
+        }
+        if ((VAR & 2) && tid < 32) {
+          // next frame's new samples: [start + N, start + N + hop) of both signals, one 128 B line per lane
+          const long long nxt = start + N + (long long)(tid & 15) * 32;
+          if (nxt < L && (tid & 15) * 32 < hop) prefetch_l1((tid < 16 ? xt : xe) + nxt);
         }
       } else {
+        // edge frame (reflect padding; < 1 % of the frames): gather through a small staging array so
+        // the 64-bit reflect arithmetic stays out of the unrolled hot path
+#pragma unroll 1
+        for (int n = tid; n < N; n += kV2Threads) {
+          const long long idx = reflect_index(start + n, L);
+          edge_raw[n] = make_float2(__ldg(xt + idx), __ldg(xe + idx));
+        }
+        __syncthreads();
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-          const long long idx = reflect_index(start + tid + 128 * r, L);
           const double w = __ldg(P.win_half + tid + 128 * r);
-          v[r] = cd{w * (double)__ldg(xt + idx), w * (double)__ldg(xe + idx)};
+          const float2 x = edge_raw[tid + 128 * r];
+          v[r] = cd{w * (double)x.x, w * (double)x.y};
         }
       }
       bfly16<false>(v);
-      b1[0] = v[0];
 #pragma unroll
-      for (int q = 1; q < 16; ++q) b1[144 * q] = cmul(v[q], tw1[q - 1]);
+      for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw1[q - 1]);
+      // the previous frame's pass-3 loads must be done before buf is overwritten; placed here (after
+      // this frame's loads and butterfly) the barrier finds every warp long past that point
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
       __syncthreads();
       // ---- pass 2: sub-transforms of length 128 (stride 8)
 #pragma unroll
@@ -402,7 +441,6 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
         a[r] = b3a[r];
         b[r] = b3b[r];
       }
-      __syncthreads();  // buf may now be overwritten by the next frame's pass 1
       bfly8<false>(a);
       bfly8<false>(b);
       // ---- epilogue, from registers
@@ -642,6 +680,25 @@ static bool force_generic_k1() {
   return v == 1;
 }
 
+// resident CTAs per SM the 2048 kernel is compiled for (register cap 168 at 3, 255 at 2)
+static int v2_min_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_V2_MIN_BLOCKS");
+    v = (e && e[0] == '2') ? 2 : 3;
+  }
+  return v;
+}
+
+static int v2_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_V2_VARIANT");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 struct WsLayout {
   size_t item_start, item_pair, spec_off, partials, ssim_part, spec_e, spec_t, total;
   int chunk, n_items, tiles_x, tiles_per_pair;
@@ -785,18 +842,32 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
       SSR_CUDA_TRY(cudaEventRecord(ev.first, st));
     }
     const unsigned m3 = flags & 7u;
-    if (!spec_e && !spec_t && m3 == 1u)
-      k_stft_metrics_2048<1><<<g2, kV2Threads, 0, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair,
-                                                        w.n_items, w.chunk, flags, partials, spec_e,
-                                                        spec_t, spec_off);
-    else if (!spec_e && !spec_t && m3 == 7u)
-      k_stft_metrics_2048<7><<<g2, kV2Threads, 0, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair,
-                                                        w.n_items, w.chunk, flags, partials, spec_e,
-                                                        spec_t, spec_off);
-    else
-      k_stft_metrics_2048<-1><<<g2, kV2Threads, 0, st>>>(plan->dev, est, tgt, offs_dev, item_start,
-                                                         item_pair, w.n_items, w.chunk, flags, partials,
-                                                         spec_e, spec_t, spec_off);
+    const size_t smem2 = sizeof(cd) * (2048 + 256) + sizeof(float2) * 2048;
+    const int fixed = (!spec_e && !spec_t && m3 == 1u) ? 1 : ((!spec_e && !spec_t && m3 == 7u) ? 7 : -1);
+    const int minb = v2_min_blocks();
+    if (g2 > sms * minb) g2 = sms * minb;
+#define SSR_V2_LAUNCH(FX, MB, VR)                                                                      \
+  do {                                                                                              \
+    auto kern = k_stft_metrics_2048<FX, MB, VR>;                                                       \
+    SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+    kern<<<g2, kV2Threads, smem2, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
+                                        w.chunk, flags, partials, spec_e, spec_t, spec_off);        \
+  } while (0)
+    const int var = v2_variant();
+    if (minb == 2) {
+      if (fixed == 1) SSR_V2_LAUNCH(1, 2, 0);
+      else if (fixed == 7) SSR_V2_LAUNCH(7, 2, 0);
+      else SSR_V2_LAUNCH(-1, 2, 0);
+    } else if (fixed == 1) {
+      if (var == 1) SSR_V2_LAUNCH(1, 3, 1);
+      else if (var == 2) SSR_V2_LAUNCH(1, 3, 2);
+      else if (var == 3) SSR_V2_LAUNCH(1, 3, 3);
+      else SSR_V2_LAUNCH(1, 3, 0);
+    } else {
+      if (fixed == 7) SSR_V2_LAUNCH(7, 3, 2);
+      else SSR_V2_LAUNCH(-1, 3, 2);
+    }
+#undef SSR_V2_LAUNCH
     SSR_LAUNCH_CHECK("k_stft_metrics_2048");
     if (tm.on) {
       SSR_CUDA_TRY(cudaEventRecord(ev.second, st));

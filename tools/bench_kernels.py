@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Per-kernel device timings (CUDA events) at BASELINE-shaped sizes; prints one JSON line per case.
+Not the contract benchmark (that is bench.py) -- used to fill DESIGN.md and to steer optimisation."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ssr_eval_b200 import _native as N  # noqa: E402
+from ssr_eval_b200.engine import StftMetrics, PolyphaseResampler, HardLowpass, offsets_of  # noqa: E402
+
+dev = torch.device("cuda", 0)
+PEAK = 6582.5
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def report(name, ms, units, unit_name, alg_bytes):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"case": name, "ms": round(ms, 4), unit_name + "_per_s": round(units / (ms * 1e-3), 1),
+                      "algorithmic_GBps": round(gbs, 1), "frac_of_measured_hbm_peak": round(gbs / PEAK, 4)}), flush=True)
+
+
+def main():
+    which = set(sys.argv[1:]) or {"k1", "k1blue", "k3", "k4"}
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    if "k1" in which:
+        n, L = 1024, 240000
+        tgt = 0.1 * torch.randn(n * L, generator=g, device=dev)
+        est = tgt + 1e-3 * torch.randn(n * L, generator=g, device=dev)
+        off = offsets_of([L] * n)
+        off_d = torch.from_numpy(off).to(dev)
+        eng = StftMetrics(2048, 512)
+        out = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        for flags, name in ((1, "K1 2048/512 LSD"), (7, "K1 2048/512 LSD+log_sispec+sispec"),
+                            (15, "K1+K2 2048/512 all four (L2-sized sub-batches)")):
+            ms = timeit(lambda: eng.metrics_device(est, tgt, off, flags, offsets_dev=off_d, out=out))
+            report(name, ms, n, "pairs", n * (8 * L + 32))
+        del tgt, est
+    if "k1blue" in which:
+        n, L = 256, 240000
+        tgt = 0.1 * torch.randn(n * L, generator=g, device=dev)
+        est = tgt + 1e-3 * torch.randn(n * L, generator=g, device=dev)
+        off = offsets_of([L] * n)
+        off_d = torch.from_numpy(off).to(dev)
+        eng = StftMetrics(2229, 480)
+        out = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        for flags, name in ((1, "K1 2229/480 (Bluestein M=8192) LSD"), (15, "K1+K2 2229/480 all four")):
+            ms = timeit(lambda: eng.metrics_device(est, tgt, off, flags, offsets_dev=off_d, out=out), iters=3, warm=1)
+            report(name, ms, n, "pairs", n * (8 * L + 32))
+        del tgt, est
+    if "k3" in which:
+        for up, down, L_in, name in ((160, 147, 220500, "K3 44.1k->48k (160/147, 3201 taps)"),
+                                     (441, 160, 80000, "K3 16k->44.1k (441/160, 8821 taps)")):
+            n = 1024
+            x = 0.1 * torch.randn(n * L_in, generator=g, device=dev)
+            rs = PolyphaseResampler(up, down)
+            off = offsets_of([L_in] * n)
+            off_d = torch.from_numpy(off).to(dev)
+            ms = timeit(lambda: rs.resample_device(x, off, off_d))
+            report(name, ms, n, "utterances", 4 * n * (L_in + rs.out_len(L_in)))
+            del x
+    if "k4" in which:
+        n, L = 1024, 220500
+        x = 0.1 * torch.randn(n * L, generator=g, device=dev)
+        lp = HardLowpass(2048, 441)
+        off = offsets_of([L] * n)
+        off_d = torch.from_numpy(off).to(dev)
+        cuts = [lp.cut_bin(12000 / 22050)] * n
+        ms = timeit(lambda: lp.apply_device(x, off, cuts, off_d))
+        report("K4 stft_hard 2048/441 (5 s @ 44.1k)", ms, n, "utterances", 8 * n * L)
+
+
+if __name__ == "__main__":
+    main()
