@@ -46,6 +46,58 @@ k_resample(const float* __restrict__ x, const long long* __restrict__ in_off, fl
   y[out_off[u] + j] = acc;
 }
 
+// Register-tiled variant.  Outputs j and j + TP (TP a multiple of `up`) share their polyphase phase, so a
+// thread keeps its phase's K <= KMAX taps in registers and produces R outputs j, j+TP, ..., j+(R-1)TP;
+// only x is loaded in the inner loop (through L1: consecutive lanes read consecutive-ish samples).
+// The float32 multiply / add order per output is unchanged (ascending input index), so results stay
+// bit-identical to scipy.
+template <int KMAX, int R>
+__global__ void __launch_bounds__(512)
+k_resample_tiled(const float* __restrict__ x, const long long* __restrict__ in_off, float* __restrict__ y,
+                 const long long* __restrict__ out_off, int u0, int up, int down, int n_pre_pad,
+                 int n_pre_remove, int K, const float* __restrict__ bank) {
+  const int u = u0 + blockIdx.y;
+  const long long n_out = out_off[u + 1] - out_off[u];
+  const int TP = blockDim.x;
+  const long long j0 = (long long)blockIdx.x * TP * R + threadIdx.x;
+  if ((long long)blockIdx.x * TP * R >= n_out) return;
+  const long long n_in = in_off[u + 1] - in_off[u];
+  const float* xu = x + in_off[u];
+  float* yu = y + out_off[u];
+  long long c = (j0 + n_pre_remove) * (long long)down - n_pre_pad;
+  long long i_hi = c / up;
+  long long phase = c - i_hi * up;
+  if (phase < 0) {
+    phase += up;
+    i_hi -= 1;
+  }
+  float h[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) h[k] = (k < K) ? __ldg(bank + phase * K + k) : 0.f;
+  const long long step = (long long)(TP / up) * down;  // input advance per TP outputs (TP % up == 0)
+#pragma unroll 1
+  for (int i = 0; i < R; ++i) {
+    const long long j = j0 + (long long)i * TP;
+    if (j < n_out) {
+      float acc = 0.f;
+      if (i_hi - (K - 1) >= 0 && i_hi < n_in) {  // interior: no bounds checks
+        const float* px = xu + i_hi;
+#pragma unroll
+        for (int k = KMAX - 1; k >= 0; --k)
+          if (k < K) acc = __fadd_rn(acc, __fmul_rn(__ldg(px - k), h[k]));
+      } else {
+#pragma unroll
+        for (int k = KMAX - 1; k >= 0; --k) {
+          const long long ii = i_hi - k;
+          if (k < K && ii >= 0 && ii < n_in) acc = __fadd_rn(acc, __fmul_rn(__ldg(xu + ii), h[k]));
+        }
+      }
+      yu[j] = acc;
+    }
+    i_hi += step;
+  }
+}
+
 }  // namespace ssr
 
 using namespace ssr;
@@ -116,6 +168,25 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
   }
   if (max_out == 0) return SSR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // tiled kernel: block = smallest multiple of `up` that is >= 256 threads (<= 512), 8 outputs per thread
+  int TP = plan->up * ((256 + plan->up - 1) / plan->up);
+  if (TP <= 512 && plan->K <= 48) {
+    constexpr int R = 8;
+    for (int u0 = 0; u0 < n; u0 += 32768) {
+      int nu = n - u0 < 32768 ? n - u0 : 32768;
+      dim3 grid((unsigned)((max_out + (long long)TP * R - 1) / ((long long)TP * R)), nu);
+      const long long* io = reinterpret_cast<const long long*>(in_offsets_dev);
+      const long long* oo = reinterpret_cast<const long long*>(out_offsets_dev);
+      if (plan->K <= 24)
+        k_resample_tiled<24, R><<<grid, TP, 0, st>>>(x_dev, io, y_dev, oo, u0, plan->up, plan->down,
+                                                     plan->n_pre_pad, plan->n_pre_remove, plan->K, plan->bank);
+      else
+        k_resample_tiled<48, R><<<grid, TP, 0, st>>>(x_dev, io, y_dev, oo, u0, plan->up, plan->down,
+                                                     plan->n_pre_pad, plan->n_pre_remove, plan->K, plan->bank);
+      SSR_LAUNCH_CHECK("k_resample_tiled");
+    }
+    return SSR_OK;
+  }
   for (int u0 = 0; u0 < n; u0 += 32768) {
     int nu = n - u0 < 32768 ? n - u0 : 32768;
     dim3 grid((unsigned)((max_out + 255) / 256), nu);

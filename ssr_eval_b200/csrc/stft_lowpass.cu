@@ -12,11 +12,13 @@
 //   -> x window / n_fft -> overlap-add in shared memory -> / clamp(sum window^2, 1e-11) -> trim.
 // A work item owns `chunk_hops` hops of output samples and recomputes the <= n_fft/hop halo frames.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "k1_map.cuh"
 
 struct ssr_lowpass_plan {
   int n_fft, hop, logM, device;
@@ -147,6 +149,222 @@ k_stft_hard_lowpass(LpDev P, const float* __restrict__ x, const long long* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Specialised n_fft = 2048 kernel (the only size the reference uses, dsp.py:9): 128 threads, radix
+// 16 x 16 x 8 forward DIF and 8 x 16 x 16 inverse DIT in float32.  As in K1 every thread owns a last-
+// pass butterfly AND its Hermitian partner (k1_map.cuh), so the split of the two packed frames, the
+// mag/cos/sin round trip, the zeroing and the re-packing all happen in registers between the forward
+// pass 3 and the inverse pass 1 -- 4 shared-memory exchanges per frame PAIR instead of 8.
+// float2 slots are padded as i + i/16 (conflict-free for the 8-byte accesses of all three passes).
+// ---------------------------------------------------------------------------------------------
+SSR_HD int pad16(int i) { return i + (i >> 4); }
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// mag = clamp(re^2+im^2, 1e-8)^0.5, cos = re/mag, sin = im/mag, out = mag*cos, mag*sin (or 0)
+__device__ __forceinline__ cf phase_roundtrip_fast(float re, float im, bool keep) {
+  const float mag = sqrt_approx(fmaxf(re * re + im * im, 1e-8f));
+  const float inv = rcp_approx(mag);
+  const float m = keep ? mag : 0.f;
+  return cf{m * (re * inv), m * (im * inv)};
+}
+
+__global__ void __launch_bounds__(kV2Threads, 3)
+k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* __restrict__ offsets,
+                         const int* __restrict__ cut_bins, float* __restrict__ y, int u0,
+                         int chunk_hops) {
+  constexpr int N = 2048;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* const buf = reinterpret_cast<cf*>(smem_raw);                       // N + N/16 slots
+  float* const acc = reinterpret_cast<float*>(smem_raw + sizeof(cf) * (N + N / 16));
+  __shared__ __align__(8) cf tw2[15 * 8];
+
+  const int tid = threadIdx.x;
+  const int u = u0 + blockIdx.y;
+  const long long off = offsets[u];
+  const long long L = offsets[u + 1] - off;
+  const int hop = P.hop;
+  const long long n0 = (long long)blockIdx.x * chunk_hops * hop;
+  if (n0 >= L) return;
+  const long long n1 = min(L, n0 + (long long)chunk_hops * hop);
+  const long long m0 = n0 + N / 2, m1 = n1 + N / 2;
+  const int span = (int)(m1 - m0);
+  const long long T = L / hop + 1;
+  const long long f_lo = (m0 - N >= 0) ? (m0 - N) / hop + 1 : 0;
+  const long long f_hi = min(T - 1, (m1 - 1) / hop);
+  const int cut = cut_bins[u];
+  const float* xu = x + off;
+
+  cf tw1[15];
+#pragma unroll
+  for (int q = 1; q < 16; ++q) tw1[q - 1] = P.tw[tid * q];
+  if (tid < 120) tw2[tid] = P.tw[16 * (tid & 7) * ((tid >> 3) + 1)];
+  int ia, ib;
+  v2_thread_butterflies(tid, &ia, &ib);
+  const bool special = (tid == kV2Threads - 1);
+  const int ka = v2_klow(ia), kb = v2_klow(ib);
+  const int j2 = tid & 7;
+  cf* const b1 = buf + pad16(tid);                      // element tid + 128 q -> b1[136 q]
+  cf* const b2 = buf + pad16((tid >> 3) * 128 + j2);    // element base + 8 r   -> b2[8 r + r/2]
+  cf* const b3a = buf + 8 * ia + (ia >> 1);             // element 8 i + r      -> b3[r]
+  cf* const b3b = buf + 8 * ib + (ib >> 1);
+  const cf* const t2 = tw2 + j2;
+  float wn[16];  // window / n_fft of this thread's 16 output samples
+#pragma unroll
+  for (int r = 0; r < 16; ++r) wn[r] = P.win_over_n[tid + 128 * r];
+
+  for (int i = tid; i < span; i += kV2Threads) acc[i] = 0.f;
+  __syncthreads();
+
+  for (long long f = f_lo; f <= f_hi; f += 2) {
+    const bool two = (f + 1) <= f_hi;
+    const long long s0 = f * hop - N / 2, s1 = s0 + hop;
+    cf v[16];
+    // ---- forward pass 1: z = w*x_f + i*w*x_{f+1}
+    if (s0 >= 0 && s1 + N <= L) {
+      const float* p0 = xu + s0 + tid;
+      const float* p1 = xu + s1 + tid;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float w = __ldg(P.win + tid + 128 * r);
+        v[r] = cf{w * __ldg(p0 + 128 * r), two ? w * __ldg(p1 + 128 * r) : 0.f};
+      }
+    } else {
+#pragma unroll 1
+      for (int r = 0; r < 16; ++r) {
+        const float w = __ldg(P.win + tid + 128 * r);
+        const float a = w * __ldg(xu + lp_reflect(s0 + tid + 128 * r, L));
+        const float b = two ? w * __ldg(xu + lp_reflect(s1 + tid + 128 * r, L)) : 0.f;
+        // dynamic register index is avoided by a select chain on the unrolled copy below
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr)
+          if (rr == r) v[rr] = cf{a, b};
+      }
+    }
+    bfly16<false>(v);
+    b1[0] = v[0];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) b1[136 * q] = cmul(v[q], tw1[q - 1]);
+    __syncthreads();
+    // ---- forward pass 2
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = b2[8 * r + (r >> 1)];
+    bfly16<false>(v);
+    b2[0] = v[0];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) b2[8 * q + (q >> 1)] = cmul(v[q], t2[(q - 1) * 8]);
+    __syncthreads();
+    // ---- forward pass 3 (registers), bin processing, inverse pass 1 (registers)
+    cf* a = v;
+    cf* b = v + 8;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      a[r] = b3a[r];
+      b[r] = b3b[r];
+    }
+    bfly8<false>(a);
+    bfly8<false>(b);
+    auto process = [&](int k, cf& zk, cf& zn, bool self) {
+      // X_f = (Z[k] + conj Z[N-k]) / 2 ; X_{f+1} = (Z[k] - conj Z[N-k]) / (2i)
+      const float x1r = 0.5f * (zk.x + zn.x), x1i = 0.5f * (zk.y - zn.y);
+      const float x2r = 0.5f * (zk.y + zn.y), x2i = 0.5f * (zn.x - zk.x);
+      const bool keep = k < cut;
+      cf A = phase_roundtrip_fast(x1r, x1i, keep);
+      cf B = phase_roundtrip_fast(x2r, x2i, keep);
+      if (self) {  // DC / Nyquist: imaginary parts never reach the real IDFT
+        A.y = 0.f;
+        B.y = 0.f;
+      }
+      zk = cf{A.x - B.y, A.y + B.x};             // Y[k]   = A + iB
+      if (!self) zn = cf{A.x + B.y, B.x - A.y};  // Y[N-k] = conj(A) + i conj(B)
+    };
+    if (!special) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        process(ka + 256 * q, a[q], b[7 - q], false);
+        process(kb + 256 * q, b[q], a[7 - q], false);
+      }
+    } else {
+      // butterfly 0 holds k = 256 q (partner (8-q)%8 in the same butterfly), butterfly 8 holds 128 + 256 q
+      process(0, a[0], a[0], true);
+      process(256, a[1], a[7], false);
+      process(512, a[2], a[6], false);
+      process(768, a[3], a[5], false);
+      process(1024, a[4], a[4], true);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) process(128 + 256 * q, b[q], b[7 - q], false);
+    }
+    bfly8<true>(a);
+    bfly8<true>(b);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      b3a[r] = a[r];
+      b3b[r] = b[r];
+    }
+    __syncthreads();
+    // ---- inverse pass 2
+    v[0] = b2[0];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b2[8 * q + (q >> 1)], t2[(q - 1) * 8]);
+    bfly16<true>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) b2[8 * r + (r >> 1)] = v[r];
+    __syncthreads();
+    // ---- inverse pass 3 -> natural order: v[r] = sample tid + 128 r (Re: frame f, Im: frame f+1)
+    v[0] = b1[0];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b1[136 * q], tw1[q - 1]);
+    bfly16<true>(v);
+    // ---- overlap-add, frame f then frame f+1
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const long long m = f * hop + tid + 128 * r;
+      if (m >= m0 && m < m1) acc[m - m0] += wn[r] * v[r].x;
+    }
+    __syncthreads();
+    if (two) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const long long m = (f + 1) * hop + tid + 128 * r;
+        if (m >= m0 && m < m1) acc[m - m0] += wn[r] * v[r].y;
+      }
+    }
+    __syncthreads();
+  }
+
+  for (int i = tid; i < span; i += kV2Threads) {
+    const long long m = m0 + i;
+    long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
+    long long fb = min(T - 1, m / hop);
+    float ws = 0.f;
+    for (long long f = fa; f <= fb; ++f) ws += P.win_sq[m - f * hop];
+    ws = fmaxf(ws, 1e-11f);
+    y[off + (m - N / 2)] = acc[i] / ws;
+  }
+}
+
+// SSR_FORCE_GENERIC_K4=1 routes n_fft 2048 through the generic radix-8 kernel (A/B tests only)
+static bool force_generic_k4() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_FORCE_GENERIC_K4");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+static int launch_lp_2048(const ssr_lowpass_plan* plan, const float* x, const long long* offs,
+                          const int* cut, float* y, int n, long long max_len, cudaStream_t st);
+
 static int lp_chunk_hops(int hop) {
   int c = 14336 / hop;  // accumulator <= 56 KB
   if (c > 32) c = 32;
@@ -168,6 +386,23 @@ static int launch_lp(const ssr_lowpass_plan* plan, const float* x, const long lo
     int nu = n - u0 < 32768 ? n - u0 : 32768;
     kern<<<dim3(gx, nu), kLpThreads, smem, st>>>(P, x, offs, cut, y, u0, ch);
     SSR_LAUNCH_CHECK("k_stft_hard_lowpass");
+  }
+  return SSR_OK;
+}
+
+static int launch_lp_2048(const ssr_lowpass_plan* plan, const float* x, const long long* offs,
+                          const int* cut, float* y, int n, long long max_len, cudaStream_t st) {
+  LpDev P{plan->n_fft, plan->hop, plan->tw, plan->win, plan->win_over_n, plan->win_sq, plan->ppos};
+  const int ch = lp_chunk_hops(plan->hop);
+  size_t smem = sizeof(cf) * (size_t)(2048 + 128) + sizeof(float) * (size_t)ch * plan->hop;
+  SSR_CUDA_TRY(cudaFuncSetAttribute(k_stft_hard_lowpass_2048, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  long long per = (long long)ch * plan->hop;
+  unsigned gx = (unsigned)((max_len + per - 1) / per);
+  for (int u0 = 0; u0 < n; u0 += 32768) {
+    int nu = n - u0 < 32768 ? n - u0 : 32768;
+    k_stft_hard_lowpass_2048<<<dim3(gx, nu), kV2Threads, smem, st>>>(P, x, offs, cut, y, u0, ch);
+    SSR_LAUNCH_CHECK("k_stft_hard_lowpass_2048");
   }
   return SSR_OK;
 }
@@ -261,7 +496,9 @@ int ssr_stft_hard_lowpass_batched(const ssr_lowpass_plan* plan, const float* x_d
     case 8: return launch_lp<8>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
     case 9: return launch_lp<9>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
     case 10: return launch_lp<10>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
-    case 11: return launch_lp<11>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
+    case 11:
+      if (!force_generic_k4()) return launch_lp_2048(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
+      return launch_lp<11>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
     case 12: return launch_lp<12>(plan, x_dev, offs, cut_bins_dev, y_dev, n, max_len, st);
     default: return fail(SSR_ERR_INVALID, "unsupported n_fft");
   }

@@ -50,7 +50,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kMaxChunk = 64;   // frames per work item (upper bound)
 constexpr int kPartials = 8;    // doubles per work item
 constexpr int kSsimTR = 64;     // SSIM tile: output rows
-constexpr int kSsimTC = 128;    // SSIM tile: output cols (= threads)
+constexpr int kSsimTC = 256;    // SSIM tile: output cols (2 per thread)
 
 struct StftDev {
   int n_fft, hop, F, M;
@@ -323,8 +323,9 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
 //           further shared-memory traffic.
 // Shared-memory traffic per frame: 2 exchanges (4 x 32 KB) + 30 KB of twiddles.
 // ---------------------------------------------------------------------------------------------
-// FIXED >= 0: the metric flags are the compile-time constant FIXED and no spectrogram is stored
-// (hot configurations: 1 = LSD only, 7 = LSD + log-sispec + sispec); FIXED < 0: run-time flags.
+// FIXED >= 0: the metric flags are the compile-time constant FIXED (bit 3 = the magnitude
+// spectrograms are written for K2); hot configurations: 1 = LSD only, 7 = LSD + log-sispec + sispec,
+// 15 = those + spectrograms.  FIXED < 0: run-time flags.
 // VAR: experimental variants (bit 0: float->double input conversion with integer ops on the ALU
 // pipe instead of F2F on the XU pipe; bit 1: L1 prefetch of the next frame's new samples).
 template <int FIXED, int MINB, int VAR>
@@ -338,6 +339,8 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* const buf = reinterpret_cast<cd*>(smem_raw);                                // N + N/8 slots
   float2* const edge_raw = reinterpret_cast<float2*>(smem_raw + sizeof(cd) * (N + N / 8));  // N pairs
+  float* const row_t = reinterpret_cast<float*>(edge_raw + N);  // magnitude rows of the last frame
+  float* const row_e = row_t + 1104;
   __shared__ __align__(16) cd tw2[15 * 8];
   __shared__ float lsd_part[kMaxChunk][NW];
   __shared__ double red[NW][kPartials];
@@ -347,7 +350,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
   if (FIXED >= 0) flags = (unsigned)FIXED;
   const bool want_lsd = flags & SSR_METRIC_LSD, want_log = flags & SSR_METRIC_LOG_SISPEC,
              want_lin = flags & SSR_METRIC_SISPEC;
-  if (FIXED >= 0) {
+  if (FIXED >= 0 && !(FIXED & 8)) {
     spec_e = nullptr;
     spec_t = nullptr;
   }
@@ -381,6 +384,8 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
     const float* xe = est + off;
     const float* xt = tgt + off;
     double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
+    float* pend_t = nullptr;
+    float* pend_e = nullptr;
 
     for (int fi = 0; fi < nf; ++fi) {
       const long long f = f0 + fi;
@@ -422,6 +427,13 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       // the previous frame's pass-3 loads must be done before buf is overwritten; placed here (after
       // this frame's loads and butterfly) the barrier finds every warp long past that point
       __syncthreads();
+      if (pend_t) {  // coalesced copy-out of the previous frame's magnitude rows (all epilogues are done)
+        for (int k = tid; k < F; k += kV2Threads) {
+          pend_t[k] = row_t[k + (k >> 4)];
+          if (pend_e) pend_e[k] = row_e[k + (k >> 4)];
+        }
+        pend_t = nullptr;
+      }
 #pragma unroll
       for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
       __syncthreads();
@@ -445,8 +457,8 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       bfly8<false>(b);
       // ---- epilogue, from registers
       float lsd_acc = 0.f;
-      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
       float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
+      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
       auto emit = [&](int k, cd zk, cd zn) {
         // T = (Z[k] + conj Z[N-k]) / 2,  E = (Z[k] - conj Z[N-k]) / (2i); the 1/2 is in the window.
         // complex64 rounding as librosa stores it, then float32 arithmetic as torch runs it; the
@@ -463,8 +475,10 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
         const float me = __fsqrt_approx(ey);
         const float mt = (st || want_lin || want_log) ? __fsqrt_approx(tx) : 0.f;
 #endif
-        if (st) st[k] = mt;
-        if (se) se[k] = me;
+        if (st) {  // staged through shared memory (slot k + k/16: conflict-free for the scattered k of a warp)
+          row_t[k + (k >> 4)] = mt;
+          row_e[k + (k >> 4)] = me;
+        }
         if (want_lsd) {
           const float den = me + 1e-12f;
 #ifdef SSR_EXACT_F32_EPILOGUE
@@ -503,8 +517,17 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
         const float w = warp_sum(lsd_acc);
         if (lane == 0) lsd_part[fi][warp] = w;
       }
+      pend_t = st;  // copied out after the next barrier (next frame's pass 1, or the item epilogue)
+      pend_e = se;
     }
     __syncthreads();
+    if (pend_t) {
+      for (int k = tid; k < F; k += kV2Threads) {
+        pend_t[k] = row_t[k + (k >> 4)];
+        if (pend_e) pend_e[k] = row_e[k + (k >> 4)];
+      }
+      pend_t = nullptr;
+    }
     // ---- per-item reduction -> partials[item][0..7]
     double lsd_sum = 0.0;
     if (want_lsd && tid < nf) {
@@ -533,10 +556,16 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
 // ---------------------------------------------------------------------------------------------
 // K2: SSIM of two (T, F) float32 magnitude images, valid 7x7 windows only (skimage crops the
 // 3-pixel border, so the reflect boundary mode of uniform_filter never reaches the mean).
-// One CTA = one tile of kSsimTR x kSsimTC window positions; each thread owns one column and
-// slides down the rows keeping the last 7 horizontal 7-sums of (x, y, xx, yy, xy) in registers.
+// One CTA = one tile of kSsimTR x kSsimTC window positions, 128 threads, TWO adjacent columns per
+// thread.  Rows stream through a double-buffered shared row buffer; per row a thread forms the
+// horizontal 7-sums of (x, y, xx, yy, xy) for its two columns (sliding: the second column reuses the
+// first column's inner sum) and updates RUNNING vertical 7-sums: V += h_new - h_oldest, with the last
+// seven h kept in a register ring (unrolled-by-7 loop).  The running sums restart in every tile, so
+// the result does not depend on how the batch was partitioned.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSsimTC)
+constexpr int kSsimThreads = 128;
+
+__global__ void __launch_bounds__(kSsimThreads)
 k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
        const long long* __restrict__ spec_off, const long long* __restrict__ offsets, int pair0,
        int n_fft, int hop, int F, int tiles_x, int tiles_per_pair, double* __restrict__ ssim_part) {
@@ -553,70 +582,106 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   }
   const int r_end = min(r0 + kSsimTR, rows_out) + 6;  // input rows [r0, r_end)
   const int c0 = tx * kSsimTC;
-  const int c = threadIdx.x;
-  const bool col_ok = (c0 + c) < cols_out;
+  const int t = threadIdx.x;
+  const int c = 2 * t;  // first of this thread's two columns inside the tile
+  const bool ok0 = (c0 + c) < cols_out, ok1 = (c0 + c + 1) < cols_out;
   const float* E = spec_e + spec_off[p];
   const float* G = spec_t + spec_off[p];
-  __shared__ float rowbuf[2][2][kSsimTC + 8];
-  __shared__ double red[kSsimTC / 32];
+  constexpr int RB = kSsimTC + 8;
+  __shared__ __align__(16) float rowbuf[2][2][RB];
+  __shared__ double red[kSsimThreads / 32];
 
-  float hx[7], hy[7], hxx[7], hyy[7], hxy[7];
+  float ring[7][10];
 #pragma unroll
-  for (int s = 0; s < 7; ++s) hx[s] = hy[s] = hxx[s] = hyy[s] = hxy[s] = 0.f;
+  for (int s = 0; s < 7; ++s)
+#pragma unroll
+    for (int q = 0; q < 10; ++q) ring[s][q] = 0.f;
+  float V[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) V[q] = 0.f;
   float acc = 0.f;
   const float inv49 = 1.0f / 49.0f, cov_norm = 49.0f / 48.0f;
   const float C1 = 0.0004f, C2 = 0.0036f;  // (0.01*2)^2, (0.03*2)^2
 
+  float pre_e[3], pre_g[3];
+  auto fetch_row = [&](int r) {
+    const float* er = E + (long long)r * F + c0;
+    const float* gr = G + (long long)r * F + c0;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int col = t + u * kSsimThreads;
+      const bool in = (u < 2 || t < 8) && (c0 + col) < F;
+      pre_e[u] = in ? __ldg(er + col) : 0.f;
+      pre_g[u] = in ? __ldg(gr + col) : 0.f;
+    }
+  };
+  fetch_row(r0);
   for (int rb = r0; rb < r_end; rb += 7) {
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
       const int r = rb + s;
       if (r < r_end) {  // uniform across the CTA
         const int par = (r - r0) & 1;
-        const float* er = E + (long long)r * F;
-        const float* gr = G + (long long)r * F;
-        int col = c0 + c;
-        rowbuf[par][0][c] = col < F ? er[col] : 0.f;
-        rowbuf[par][1][c] = col < F ? gr[col] : 0.f;
-        if (c < 6) {
-          col = c0 + kSsimTC + c;
-          rowbuf[par][0][kSsimTC + c] = col < F ? er[col] : 0.f;
-          rowbuf[par][1][kSsimTC + c] = col < F ? gr[col] : 0.f;
+        // tile row (kSsimTC + 6 values per image, zero beyond the image) was fetched one row ahead
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int col = t + u * kSsimThreads;
+          if (u < 2 || t < 8) {
+            rowbuf[par][0][col] = pre_e[u];
+            rowbuf[par][1][col] = pre_g[u];
+          }
         }
         __syncthreads();
-        float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+        if (r + 1 < r_end) fetch_row(r + 1);
+        float x[8], y[8];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          float x = rowbuf[par][0][c + j], y = rowbuf[par][1][c + j];
-          sx += x;
-          sy += y;
-          sxx += x * x;
-          syy += y * y;
-          sxy += x * y;
+        for (int j = 0; j < 4; ++j) {
+          const float2 xv = *reinterpret_cast<const float2*>(&rowbuf[par][0][c + 2 * j]);
+          const float2 yv = *reinterpret_cast<const float2*>(&rowbuf[par][1][c + 2 * j]);
+          x[2 * j] = xv.x;
+          x[2 * j + 1] = xv.y;
+          y[2 * j] = yv.x;
+          y[2 * j + 1] = yv.y;
         }
-        hx[s] = sx;
-        hy[s] = sy;
-        hxx[s] = sxx;
-        hyy[s] = syy;
-        hxy[s] = sxy;
-        if (r - r0 >= 6 && col_ok) {
-          float vx_ = 0.f, vy_ = 0.f, vxx = 0.f, vyy = 0.f, vxy_ = 0.f;
+        // inner sums over columns c+1 .. c+6, then the two outputs add their own end column
+        float ix = 0.f, iy = 0.f, ixx = 0.f, iyy = 0.f, ixy = 0.f;
 #pragma unroll
-          for (int q = 0; q < 7; ++q) {
-            vx_ += hx[q];
-            vy_ += hy[q];
-            vxx += hxx[q];
-            vyy += hyy[q];
-            vxy_ += hxy[q];
+        for (int j = 1; j < 7; ++j) {
+          ix += x[j];
+          iy += y[j];
+          ixx += x[j] * x[j];
+          iyy += y[j] * y[j];
+          ixy += x[j] * y[j];
+        }
+        float h[10];
+        h[0] = ix + x[0];
+        h[1] = iy + y[0];
+        h[2] = ixx + x[0] * x[0];
+        h[3] = iyy + y[0] * y[0];
+        h[4] = ixy + x[0] * y[0];
+        h[5] = ix + x[7];
+        h[6] = iy + y[7];
+        h[7] = ixx + x[7] * x[7];
+        h[8] = iyy + y[7] * y[7];
+        h[9] = ixy + x[7] * y[7];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          V[q] += h[q] - ring[s][q];
+          ring[s][q] = h[q];
+        }
+        if (r - r0 >= 6) {
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const float ux = V[5 * o] * inv49, uy = V[5 * o + 1] * inv49;
+            const float uxx = V[5 * o + 2] * inv49, uyy = V[5 * o + 3] * inv49, uxy = V[5 * o + 4] * inv49;
+            const float vx = cov_norm * (uxx - ux * ux);
+            const float vy = cov_norm * (uyy - uy * uy);
+            const float vxy = cov_norm * (uxy - ux * uy);
+            const float A1 = 2.f * ux * uy + C1, A2 = 2.f * vxy + C2;
+            const float B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+            const float S = __fdividef(A1 * A2, B1 * B2);
+            if (o == 0 ? ok0 : ok1) acc += S;
           }
-          float ux = vx_ * inv49, uy = vy_ * inv49;
-          float uxx = vxx * inv49, uyy = vyy * inv49, uxy = vxy_ * inv49;
-          float vx = cov_norm * (uxx - ux * ux);
-          float vy = cov_norm * (uyy - uy * uy);
-          float vxy = cov_norm * (uxy - ux * uy);
-          float A1 = 2.f * ux * uy + C1, A2 = 2.f * vxy + C2;
-          float B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
-          acc += (A1 * A2) / (B1 * B2);
         }
       }
     }
@@ -625,9 +690,9 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = r;
   __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < kSsimTC / 32; ++w) s += red[w];
-    *out = s;
+    double sum = 0.0;
+    for (int w = 0; w < kSsimThreads / 32; ++w) sum += red[w];
+    *out = sum;
   }
 }
 
@@ -643,28 +708,34 @@ __device__ inline double sispec_from_sums(double s_et, double s_tt, double s_ee)
   return 10.0 * log10(tt / (nn + EPS) + EPS);
 }
 
-__global__ void k_finalize(const long long* __restrict__ offsets, int n, int n_fft, int hop, int F,
-                           const int* __restrict__ item_start, const double* __restrict__ partials,
-                           const double* __restrict__ ssim_part, int tiles_per_pair, unsigned flags,
-                           double* __restrict__ out) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+k_finalize(const long long* __restrict__ offsets, int n, int n_fft, int hop, int F,
+           const int* __restrict__ item_start, const double* __restrict__ partials,
+           const double* __restrict__ ssim_part, int tiles_per_pair, unsigned flags,
+           double* __restrict__ out) {
+  // one warp per pair; lanes stride over the items / tiles, then a fixed-shape shuffle tree:
+  // the summation order depends only on the pair's own item / tile count
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (p >= n) return;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
+  const long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
   double v[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (int it = item_start[p]; it < item_start[p + 1]; ++it)
+  for (int it = item_start[p] + lane; it < item_start[p + 1]; it += 32)
+#pragma unroll
     for (int i = 0; i < 7; ++i) v[i] += partials[(size_t)it * kPartials + i];
+  double s = 0.0;
+  if (flags & SSR_METRIC_SSIM)
+    for (int t = lane; t < tiles_per_pair; t += 32) s += ssim_part[(size_t)p * tiles_per_pair + t];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) v[i] = warp_sum(v[i]);
+  s = warp_sum(s);
+  if (lane != 0) return;
   out[p * 4 + 0] = (flags & SSR_METRIC_LSD) ? v[0] / (double)T : nan;
   out[p * 4 + 1] = (flags & SSR_METRIC_LOG_SISPEC) ? sispec_from_sums(v[4], v[5], v[6]) : nan;
   out[p * 4 + 2] = (flags & SSR_METRIC_SISPEC) ? sispec_from_sums(v[1], v[2], v[3]) : nan;
-  if (flags & SSR_METRIC_SSIM) {
-    double s = 0.0;
-    for (int t = 0; t < tiles_per_pair; ++t) s += ssim_part[(size_t)p * tiles_per_pair + t];
-    double cnt = (double)(T - 6) * (double)(F - 6);
-    out[p * 4 + 3] = (T > 6 && F > 6) ? s / cnt : nan;
-  } else {
-    out[p * 4 + 3] = nan;
-  }
+  const double cnt = (double)(T - 6) * (double)(F - 6);
+  out[p * 4 + 3] = ((flags & SSR_METRIC_SSIM) && T > 6 && F > 6) ? s / cnt : nan;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -842,8 +913,9 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
       SSR_CUDA_TRY(cudaEventRecord(ev.first, st));
     }
     const unsigned m3 = flags & 7u;
-    const size_t smem2 = sizeof(cd) * (2048 + 256) + sizeof(float2) * 2048;
-    const int fixed = (!spec_e && !spec_t && m3 == 1u) ? 1 : ((!spec_e && !spec_t && m3 == 7u) ? 7 : -1);
+    const size_t smem2 = sizeof(cd) * (2048 + 256) + sizeof(float2) * 2048 + sizeof(float) * 2 * 1104;
+    const bool store = spec_e || spec_t;
+    const int fixed = (!store && m3 == 1u) ? 1 : ((!store && m3 == 7u) ? 7 : ((spec_e && spec_t && m3 == 7u) ? 15 : -1));
     const int minb = v2_min_blocks();
     if (g2 > sms * minb) g2 = sms * minb;
 #define SSR_V2_LAUNCH(FX, MB, VR)                                                                      \
@@ -865,6 +937,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
       else SSR_V2_LAUNCH(1, 3, 0);
     } else {
       if (fixed == 7) SSR_V2_LAUNCH(7, 3, 2);
+      else if (fixed == 15) SSR_V2_LAUNCH(15, 3, 2);
       else SSR_V2_LAUNCH(-1, 3, 2);
     }
 #undef SSR_V2_LAUNCH
@@ -1020,13 +1093,13 @@ int ssr_stft_metrics_batched(const ssr_stft_plan* plan, const float* est_dev, co
     for (int p0 = 0; p0 < n_pairs; p0 += 32768) {
       int np = n_pairs - p0 < 32768 ? n_pairs - p0 : 32768;
       dim3 grid(w.tiles_per_pair, np);
-      k_ssim<<<grid, kSsimTC, 0, st>>>(spec_e, spec_t, reinterpret_cast<long long*>(ws + w.spec_off),
+      k_ssim<<<grid, kSsimThreads, 0, st>>>(spec_e, spec_t, reinterpret_cast<long long*>(ws + w.spec_off),
                                        offs, p0, plan->n_fft, plan->hop, plan->F, w.tiles_x,
                                        w.tiles_per_pair, ssim_part);
       SSR_LAUNCH_CHECK("k_ssim");
     }
   }
-  k_finalize<<<(n_pairs + 127) / 128, 128, 0, st>>>(
+  k_finalize<<<(n_pairs + 3) / 4, 128, 0, st>>>(
       offs, n_pairs, plan->n_fft, plan->hop, plan->F, reinterpret_cast<int*>(ws + w.item_start),
       reinterpret_cast<double*>(ws + w.partials), ssim_part, w.tiles_per_pair, flags, out_dev);
   SSR_LAUNCH_CHECK("k_finalize");

@@ -58,8 +58,9 @@ class _Workspace:
 class StftMetrics:
     """K1+K2: batched STFT -> {lsd, log_sispec, sispec, ssim} (ssr_eval/metrics.py:92-132)."""
 
-    # spectrogram workspace kept around the L2 size so the K1 -> K2 round trip stays on chip
-    SSIM_SUBBATCH_BYTES = 96 << 20
+    # cap of the spectrogram workspace per launch sequence (SSIM only).  Measured: L2-sized sub-batches
+    # (96 MB) lose more to launch overhead than the HBM round trip of 7.7 MB/pair costs at 6.5 TB/s.
+    SSIM_SUBBATCH_BYTES = 8 << 30
 
     def __init__(self, n_fft, hop, window=None):
         _require_cuda()

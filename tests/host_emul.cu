@@ -194,9 +194,37 @@ static int check_v2() {
   return (bad == 0 && maxerr < 1e-10) ? 0 : 1;
 }
 
+
+// forward DIF (16,16,8) followed by inverse DIT (8,16,16) must give N * identity (float and double)
+template <typename T>
+static int check_v2_roundtrip() {
+  const int N = 2048;
+  std::vector<C2<T>> tw(N), buf(padded_size(N)), x(N);
+  for (int n = 0; n < N; ++n) {
+    long double a = -2 * kPiL * n / N;
+    tw[n] = C2<T>{(T)cosl(a), (T)sinl(a)};
+    x[n] = C2<T>{(T)frand(), (T)frand()};
+    buf[pad_idx(n)] = x[n];
+  }
+  for (int tid = 0; tid < 128; ++tid) dif_pass<16>(buf.data(), N, 2048, tw.data(), tid, 128);
+  for (int tid = 0; tid < 128; ++tid) dif_pass<16>(buf.data(), N, 128, tw.data(), tid, 128);
+  for (int tid = 0; tid < 128; ++tid) dif_pass<8>(buf.data(), N, 8, tw.data(), tid, 128);
+  for (int tid = 0; tid < 128; ++tid) dit_pass<8>(buf.data(), N, 8, tw.data(), tid, 128);
+  for (int tid = 0; tid < 128; ++tid) dit_pass<16>(buf.data(), N, 128, tw.data(), tid, 128);
+  for (int tid = 0; tid < 128; ++tid) dit_pass<16>(buf.data(), N, 2048, tw.data(), tid, 128);
+  double err = 0;
+  for (int n = 0; n < N; ++n)
+    err = fmax(err, fmax(fabs((double)buf[pad_idx(n)].x / N - (double)x[n].x), fabs((double)buf[pad_idx(n)].y / N - (double)x[n].y)));
+  const double tol = sizeof(T) == 4 ? 2e-6 : 1e-14;
+  printf("v2 roundtrip (%s): maxerr %.3e\n", sizeof(T) == 4 ? "float" : "double", err);
+  return err < tol ? 0 : 1;
+}
+
 int main() {
   int bad = 0;
   bad += check_v2();
+  bad += check_v2_roundtrip<double>();
+  bad += check_v2_roundtrip<float>();
   bad += check_fft<8>();
   bad += check_fft<9>();
   bad += check_fft<10>();
