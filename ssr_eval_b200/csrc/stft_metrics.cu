@@ -62,12 +62,25 @@ struct StftDev {
   const cd* cpost;         // bluestein: chirp[k]
 };
 
+// tables of the PFA path (n_fft = R * P, P <= 1024; see stft_tables.hpp)
+struct PfaDev {
+  int n_fft, hop, F, R, P;
+  const cd* tw;     // exp(-2 pi i n / 2048)
+  const cd* cwin;   // [r*P + n] = 0.5 * window[R n + r] * chirp_P[n]
+  const cd* post;   // [r*P + k] = chirp_P[k] * W_N^{rk}
+  const cd* bfilt;  // Bluestein filter spectrum / 2048, DIF (16,16,8) order
+  const cd* wr;     // [r*R + m] = W_R^{rm}
+};
+
 }  // namespace ssr
 
 struct ssr_stft_plan {
   int n_fft, hop, F, M, logM, bluestein, device;
-  void* blob;  // one device allocation holding all tables
+  int pfa;          // 1: PFA path (pdev valid)
+  void* blob;       // one device allocation holding all tables
+  void* blob_pfa;
   ssr::StftDev dev;
+  ssr::PfaDev pdev;
 };
 
 namespace ssr {
@@ -554,6 +567,227 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1 for non-power-of-two n_fft = R * P (2229 = 3 x 743 at 48 kHz -- the reference's own default --,
+// 1114, 743, 1486 ...): R Bluestein sub-transforms of length P on the 2048-point radix 16x16x8
+// machinery of k_stft_metrics_2048 (forward DIF, filter multiply and inverse butterfly of the last /
+// first pass in registers, inverse DIT), recombined with a radix-R butterfly on the fly in the
+// epilogue.  ~6 FFT-2048 per frame instead of 2 FFT-8192 (1.6x fewer flops, 2x less shared traffic
+// than the generic Bluestein kernel).  NQ = ceil(P / 128): pass-1 inputs / pass-3' outputs beyond
+// NQ are structurally zero / unused and are pruned at compile time.
+// ---------------------------------------------------------------------------------------------
+template <int NQ, int FIXED>
+__global__ void __launch_bounds__(kV2Threads, 2)
+k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restrict__ tgt,
+                   const long long* __restrict__ offsets, const int* __restrict__ item_start,
+                   const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
+                   double* __restrict__ partials, float* __restrict__ spec_e,
+                   float* __restrict__ spec_t, const long long* __restrict__ spec_off) {
+  constexpr int M = 2048, NW = kV2Threads / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* const buf = reinterpret_cast<cd*>(smem_raw);                       // M + M/8 slots
+  cd* const Y = reinterpret_cast<cd*>(smem_raw + sizeof(cd) * (M + M / 8));  // n_fft values
+  __shared__ __align__(16) cd tw2[15 * 8];
+  __shared__ __align__(16) cd wr_s[16];
+  __shared__ float lsd_part[kMaxChunk][NW];
+  __shared__ double red[NW][kPartials];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = D.n_fft, F = D.F, hop = D.hop, R = D.R, P = D.P;
+  if (FIXED >= 0) flags = (unsigned)FIXED;
+  const bool want_lsd = flags & SSR_METRIC_LSD, want_log = flags & SSR_METRIC_LOG_SISPEC,
+             want_lin = flags & SSR_METRIC_SISPEC;
+  if (FIXED >= 0) {
+    spec_e = nullptr;
+    spec_t = nullptr;
+  }
+
+  cd tw1[15];
+#pragma unroll
+  for (int q = 1; q < 16; ++q) tw1[q - 1] = D.tw[tid * q];
+  if (tid < 120) tw2[tid] = D.tw[16 * (tid & 7) * ((tid >> 3) + 1)];
+  if (tid < R * R) wr_s[tid] = D.wr[tid];
+  int ia, ib;
+  v2_thread_butterflies(tid, &ia, &ib);
+  const int j2 = tid & 7;
+  cd* const b1 = buf + pad_idx(tid);
+  cd* const b2 = buf + pad_idx((tid >> 3) * 128 + j2);
+  cd* const b3a = buf + 9 * ia;
+  cd* const b3b = buf + 9 * ib;
+  const cd* const t2 = tw2 + j2;
+  __syncthreads();
+
+  auto combine = [&](int kap) {  // Z[kap] = sum_r W_R^{r m} Y_r[k], kap = k + P m
+    int m = 0;
+    while (kap >= P) {
+      kap -= P;
+      ++m;
+    }
+    cd z = Y[kap];
+    if (R > 1) {
+      z = cmul(z, wr_s[m]);
+      for (int r = 1; r < R; ++r) {
+        const cd t = cmul(Y[r * P + kap], wr_s[r * R + m]);
+        z = cadd(z, t);
+      }
+    }
+    return z;
+  };
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int p = item_pair[item];
+    const int c = item - item_start[p];
+    const long long off = offsets[p];
+    const long long L = offsets[p + 1] - off;
+    const long long T = stft_frames(L, N, hop);
+    const long long f0 = (long long)c * chunk;
+    const int nf = (int)min((long long)chunk, T - f0);
+    const float* xe = est + off;
+    const float* xt = tgt + off;
+    double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
+
+    for (int fi = 0; fi < nf; ++fi) {
+      const long long f = f0 + fi;
+      const long long start = f * hop - N / 2;
+      const bool interior = (start >= 0 && start + N <= L);
+      for (int r = 0; r < R; ++r) {
+        cd v[16];
+        // ---- forward pass 1: a[n] = z[R n + r] * (0.5 window * chirp), zero padded to 2048
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          v[q] = cd{0.0, 0.0};
+          if (q < NQ) {
+            const int n = tid + 128 * q;
+            if (n < P) {
+              const long long si = start + (long long)R * n + r;
+              const long long idx = interior ? si : reflect_index(si, L);
+              const double tt = (double)__ldg(xt + idx), ee = (double)__ldg(xe + idx);
+              const cd w = D.cwin[r * P + n];
+              v[q] = cd{tt * w.x - ee * w.y, tt * w.y + ee * w.x};
+            }
+          }
+        }
+        bfly16<false>(v);
+#pragma unroll
+        for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw1[q - 1]);
+        __syncthreads();  // previous sub-transform's last loads are done
+#pragma unroll
+        for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
+        __syncthreads();
+        // ---- forward pass 2
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = b2[9 * q];
+        bfly16<false>(v);
+        b2[0] = v[0];
+#pragma unroll
+        for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
+        __syncthreads();
+        // ---- forward pass 3, Bluestein filter, inverse pass 1: all in registers
+        cd* a = v;
+        cd* b = v + 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          a[q] = b3a[q];
+          b[q] = b3b[q];
+        }
+        bfly8<false>(a);
+        bfly8<false>(b);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          a[q] = cmul(a[q], D.bfilt[8 * ia + q]);
+          b[q] = cmul(b[q], D.bfilt[8 * ib + q]);
+        }
+        bfly8<true>(a);
+        bfly8<true>(b);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          b3a[q] = a[q];
+          b3b[q] = b[q];
+        }
+        __syncthreads();
+        // ---- inverse pass 2
+        v[0] = b2[0];
+#pragma unroll
+        for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b2[9 * q], t2[(q - 1) * 8]);
+        bfly16<true>(v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) b2[9 * q] = v[q];
+        __syncthreads();
+        // ---- inverse pass 3 -> conv[k], k = tid + 128 q; Y_r[k] = conv[k] * chirp[k] * W_N^{rk}
+        v[0] = b1[0];
+#pragma unroll
+        for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b1[144 * q], tw1[q - 1]);
+        bfly16<true>(v);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int k = tid + 128 * q;
+          if (k < P) Y[r * P + k] = cmul(v[q], D.post[r * P + k]);
+        }
+      }
+      __syncthreads();
+      // ---- epilogue over the F bins (recombination on the fly)
+      float lsd_acc = 0.f;
+      float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
+      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
+      for (int k = tid; k < F; k += kV2Threads) {
+        const cd zk = combine(k);
+        const cd zn = combine(k ? N - k : 0);
+        const float tre = (float)(zk.x + zn.x), tim = (float)(zk.y - zn.y);
+        const float ere = (float)(zk.y + zn.y), eim = (float)(zn.x - zk.x);
+        const float tx = tre * tre + tim * tim;
+        const float ey = ere * ere + eim * eim;
+        const float me = __fsqrt_approx(ey);
+        const float mt = (st || want_lin || want_log) ? __fsqrt_approx(tx) : 0.f;
+        if (st) st[k] = mt;
+        if (se) se[k] = me;
+        if (want_lsd) {
+          const float den = me + 1e-12f;
+          const float l = __log10f(__fdividef(tx, den * den) + 1e-12f);
+          lsd_acc += l * l;
+        }
+        if (want_lin) {
+          const double de = (double)me, dt = (double)mt;
+          s_et = fma(de, dt, s_et);
+          s_tt = fma(dt, dt, s_tt);
+          s_ee = fma(de, de, s_ee);
+        }
+        if (want_log) {
+          const double le = (double)__log10f(me + 1e-12f), lt = (double)__log10f(mt + 1e-12f);
+          l_et = fma(le, lt, l_et);
+          l_tt = fma(lt, lt, l_tt);
+          l_ee = fma(le, le, l_ee);
+        }
+      }
+      if (want_lsd) {
+        const float w = warp_sum(lsd_acc);
+        if (lane == 0) lsd_part[fi][warp] = w;
+      }
+    }
+    __syncthreads();
+    double lsd_sum = 0.0;
+    if (want_lsd && tid < nf) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sacc += lsd_part[tid][w];
+      lsd_sum = (double)sqrtf(sacc / (float)F);
+    }
+    double vals[7] = {lsd_sum, s_et, s_tt, s_ee, l_et, l_tt, l_ee};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const double rr = warp_sum(vals[i]);
+      if (lane == 0) red[warp][i] = rr;
+    }
+    __syncthreads();
+    if (tid < 7) {
+      double rr = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) rr += red[w][tid];
+      partials[(size_t)item * kPartials + tid] = rr;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2: SSIM of two (T, F) float32 magnitude images, valid 7x7 windows only (skimage crops the
 // 3-pixel border, so the reflect boundary mode of uniform_filter never reaches the mean).
 // One CTA = one tile of kSsimTR x kSsimTC window positions, 128 threads, TWO adjacent columns per
@@ -897,6 +1131,47 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   if (per_sm > 2) per_sm = 2;
   int grid = sms * per_sm;
   if (grid > w.n_items) grid = w.n_items;
+  if (plan->pfa && !force_generic_k1()) {
+    const size_t smem_p = sizeof(cd) * (2048 + 256) + sizeof(cd) * (size_t)plan->n_fft;
+    int gp = sms * 2;
+    if (gp > w.n_items) gp = w.n_items;
+    const bool store = spec_e || spec_t;
+    const bool lsd_only = !store && (flags & 7u) == 1u;
+    const int nq = (plan->pdev.P + 127) / 128;
+    TimingState& tm = timing();
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (tm.on) {
+      if (!tm.pool.empty()) {
+        ev = tm.pool.back();
+        tm.pool.pop_back();
+      } else {
+        SSR_CUDA_TRY(cudaEventCreate(&ev.first));
+        SSR_CUDA_TRY(cudaEventCreate(&ev.second));
+      }
+      SSR_CUDA_TRY(cudaEventRecord(ev.first, st));
+    }
+#define SSR_PFA_LAUNCH(NQ_, FX)                                                                      \
+  do {                                                                                               \
+    auto kern = k_stft_metrics_pfa<NQ_, FX>;                                                         \
+    SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
+    kern<<<gp, kV2Threads, smem_p, st>>>(plan->pdev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
+                                         w.chunk, flags, partials, spec_e, spec_t, spec_off);        \
+  } while (0)
+    if (nq <= 6) {
+      if (lsd_only) SSR_PFA_LAUNCH(6, 1);
+      else SSR_PFA_LAUNCH(6, -1);
+    } else {
+      if (lsd_only) SSR_PFA_LAUNCH(8, 1);
+      else SSR_PFA_LAUNCH(8, -1);
+    }
+#undef SSR_PFA_LAUNCH
+    SSR_LAUNCH_CHECK("k_stft_metrics_pfa");
+    if (tm.on) {
+      SSR_CUDA_TRY(cudaEventRecord(ev.second, st));
+      tm.pending.push_back(ev);
+    }
+    return SSR_OK;
+  }
   if (!plan->bluestein && plan->logM == 11 && !force_generic_k1()) {
     int g2 = sms * 3;
     if (g2 > w.n_items) g2 = w.n_items;
@@ -1034,6 +1309,49 @@ int ssr_stft_plan_create(ssr_stft_plan** out, int n_fft, int hop, const double* 
     delete p;
     return fail(SSR_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
   }
+  p->pfa = 0;
+  p->blob_pfa = nullptr;
+  PfaTables pt;
+  if (blue && build_pfa_tables(n_fft, window_host, &pt)) {
+    const int R = pt.R;
+    size_t q = 0;
+    size_t q_tw = q;
+    q = align_up(q + sizeof(cd) * 2048, 256);
+    size_t q_cw = q;
+    q = align_up(q + sizeof(cd) * (size_t)n_fft, 256);
+    size_t q_po = q;
+    q = align_up(q + sizeof(cd) * (size_t)n_fft, 256);
+    size_t q_bf = q;
+    q = align_up(q + sizeof(cd) * 2048, 256);
+    size_t q_wr = q;
+    q = align_up(q + sizeof(cd) * (size_t)(R * R), 256);
+    std::vector<unsigned char> hp(q, 0);
+    memcpy(hp.data() + q_tw, pt.tw.data(), sizeof(cd) * 2048);
+    memcpy(hp.data() + q_cw, pt.cwin.data(), sizeof(cd) * (size_t)n_fft);
+    memcpy(hp.data() + q_po, pt.post.data(), sizeof(cd) * (size_t)n_fft);
+    memcpy(hp.data() + q_bf, pt.bfilt.data(), sizeof(cd) * 2048);
+    memcpy(hp.data() + q_wr, pt.wr.data(), sizeof(cd) * (size_t)(R * R));
+    cudaError_t e2 = cudaMalloc(&p->blob_pfa, q);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(p->blob_pfa, hp.data(), q, cudaMemcpyHostToDevice);
+    if (e2 != cudaSuccess) {
+      if (p->blob_pfa) cudaFree(p->blob_pfa);
+      cudaFree(p->blob);
+      delete p;
+      return fail(SSR_ERR_CUDA, std::string("plan upload (pfa): ") + cudaGetErrorString(e2));
+    }
+    unsigned char* dp = static_cast<unsigned char*>(p->blob_pfa);
+    p->pfa = 1;
+    p->pdev.n_fft = n_fft;
+    p->pdev.hop = hop;
+    p->pdev.F = n_fft / 2 + 1;
+    p->pdev.R = R;
+    p->pdev.P = pt.P;
+    p->pdev.tw = reinterpret_cast<const cd*>(dp + q_tw);
+    p->pdev.cwin = reinterpret_cast<const cd*>(dp + q_cw);
+    p->pdev.post = reinterpret_cast<const cd*>(dp + q_po);
+    p->pdev.bfilt = reinterpret_cast<const cd*>(dp + q_bf);
+    p->pdev.wr = reinterpret_cast<const cd*>(dp + q_wr);
+  }
   unsigned char* d = static_cast<unsigned char*>(p->blob);
   p->dev.n_fft = n_fft;
   p->dev.hop = hop;
@@ -1052,6 +1370,7 @@ int ssr_stft_plan_create(ssr_stft_plan** out, int n_fft, int hop, const double* 
 int ssr_stft_plan_destroy(ssr_stft_plan* plan) {
   if (!plan) return SSR_OK;
   if (plan->blob) cudaFree(plan->blob);
+  if (plan->blob_pfa) cudaFree(plan->blob_pfa);
   delete plan;
   return SSR_OK;
 }

@@ -220,8 +220,66 @@ static int check_v2_roundtrip() {
   return err < tol ? 0 : 1;
 }
 
+
+// PFA (R x Bluestein-2048) pipeline for n_fft = R*P, emulated exactly as k_stft_metrics_pfa does it
+static int check_pfa(int n_fft) {
+  PfaTables tb;
+  if (!build_pfa_tables(n_fft, nullptr, &tb)) { printf("pfa tables failed %d\n", n_fft); return 1; }
+  const int N = n_fft, R = tb.R, P = tb.P, F = N / 2 + 1, M = 2048;
+  std::vector<float> t(N), e(N);
+  for (int n = 0; n < N; ++n) { t[n] = (float)frand(); e[n] = (float)(1e-6 * frand()); }
+  std::vector<cd> Y(N), buf(padded_size(M));
+  for (int r = 0; r < R; ++r) {
+    for (int n = 0; n < M; ++n) {
+      cd v{0, 0};
+      if (n < P) {
+        cd w = tb.cwin[r * P + n];
+        double tt = t[R * n + r], ee = e[R * n + r];
+        v = cd{tt * w.x - ee * w.y, tt * w.y + ee * w.x};
+      }
+      buf[pad_idx(n)] = v;
+    }
+    for (int tid = 0; tid < 128; ++tid) dif_pass<16>(buf.data(), M, 2048, tb.tw.data(), tid, 128);
+    for (int tid = 0; tid < 128; ++tid) dif_pass<16>(buf.data(), M, 128, tb.tw.data(), tid, 128);
+    for (int tid = 0; tid < 128; ++tid) dif_pass<8>(buf.data(), M, 8, tb.tw.data(), tid, 128);
+    for (int i = 0; i < M; ++i) buf[pad_idx(i)] = cmul(buf[pad_idx(i)], tb.bfilt[i]);
+    for (int tid = 0; tid < 128; ++tid) dit_pass<8>(buf.data(), M, 8, tb.tw.data(), tid, 128);
+    for (int tid = 0; tid < 128; ++tid) dit_pass<16>(buf.data(), M, 128, tb.tw.data(), tid, 128);
+    for (int tid = 0; tid < 128; ++tid) dit_pass<16>(buf.data(), M, 2048, tb.tw.data(), tid, 128);
+    for (int k = 0; k < P; ++k) Y[r * P + k] = cmul(buf[pad_idx(k)], tb.post[r * P + k]);
+  }
+  auto combine = [&](int kap) {
+    int k = kap % P, m = kap / P;
+    cd z{0, 0};
+    for (int r = 0; r < R; ++r) z = cadd(z, cmul(Y[r * P + k], tb.wr[r * R + m]));
+    return z;
+  };
+  double errT = 0, errE = 0, magT = 0;
+  for (int k = 0; k < F; k += 3) {
+    cd a = combine(k), b = combine((N - k) % N);
+    double tre = a.x + b.x, tim = a.y - b.y, ere = a.y + b.y, eim = b.x - a.x;
+    long double rt = 0, it = 0, re_ = 0, ie = 0;
+    for (int n = 0; n < N; ++n) {
+      long double w = 0.5L - 0.5L * cosl(2 * kPiL * n / N);
+      long double ang = -2 * kPiL * ((long long)n * k % N) / N;
+      long double c = cosl(ang), s = sinl(ang);
+      rt += w * t[n] * c; it += w * t[n] * s; re_ += w * e[n] * c; ie += w * e[n] * s;
+    }
+    errT = fmax(errT, fmax(fabs(tre - (double)rt), fabs(tim - (double)it)));
+    errE = fmax(errE, fmax(fabs(ere - (double)re_), fabs(eim - (double)ie)));
+    magT = fmax(magT, hypot((double)rt, (double)it));
+  }
+  printf("pfa n_fft=%4d = %d x %d  |T|max %.3e errT %.3e errE %.3e\n", N, R, P, magT, errT, errE);
+  return (errT < 1e-11 * (1 + magT) && errE < 1e-11 * (1 + magT)) ? 0 : 1;
+}
+
 int main() {
   int bad = 0;
+  bad += check_pfa(2229);
+  bad += check_pfa(1114);
+  bad += check_pfa(743);
+  bad += check_pfa(1486);
+  bad += check_pfa(371);
   bad += check_v2();
   bad += check_v2_roundtrip<double>();
   bad += check_v2_roundtrip<float>();
