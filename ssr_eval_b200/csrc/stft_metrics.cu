@@ -351,8 +351,8 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
   constexpr int N = 2048, F = 1025, NW = kV2Threads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* const buf = reinterpret_cast<cd*>(smem_raw);                                // N + N/8 slots
-  float2* const edge_raw = reinterpret_cast<float2*>(smem_raw + sizeof(cd) * (N + N / 8));  // N pairs
-  float* const row_t = reinterpret_cast<float*>(edge_raw + N);  // magnitude rows of the last frame
+  float2* const edge_raw = reinterpret_cast<float2*>(smem_raw);  // edge frames stage N raw pairs inside buf
+  float* const row_t = reinterpret_cast<float*>(smem_raw + sizeof(cd) * (N + N / 8));  // magnitude rows (store mode)
   float* const row_e = row_t + 1104;
   __shared__ __align__(16) cd tw2[15 * 8];
   __shared__ float lsd_part[kMaxChunk][NW];
@@ -421,6 +421,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       } else {
         // edge frame (reflect padding; < 1 % of the frames): gather through a small staging array so
         // the 64-bit reflect arithmetic stays out of the unrolled hot path
+        __syncthreads();  // the staging area aliases buf: the previous frame's pass-3 loads must be done
 #pragma unroll 1
         for (int n = tid; n < N; n += kV2Threads) {
           const long long idx = reflect_index(start + n, L);
@@ -576,7 +577,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
 // NQ are structurally zero / unused and are pruned at compile time.
 // ---------------------------------------------------------------------------------------------
 template <int NQ, int FIXED>
-__global__ void __launch_bounds__(kV2Threads, 2)
+__global__ void __launch_bounds__(kV2Threads, 3)
 k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restrict__ tgt,
                    const long long* __restrict__ offsets, const int* __restrict__ item_start,
                    const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
@@ -585,7 +586,9 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
   constexpr int M = 2048, NW = kV2Threads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* const buf = reinterpret_cast<cd*>(smem_raw);                       // M + M/8 slots
-  cd* const Y = reinterpret_cast<cd*>(smem_raw + sizeof(cd) * (M + M / 8));  // n_fft values
+  // Y_r, r < R-1, live behind buf; the LAST sub-transform's Y is written over buf itself (dead by then),
+  // which keeps the CTA at ~65 KB of shared memory = 3 CTAs per SM
+  cd* const Yx = reinterpret_cast<cd*>(smem_raw + sizeof(cd) * (M + M / 8));
   __shared__ __align__(16) cd tw2[15 * 8];
   __shared__ __align__(16) cd wr_s[16];
   __shared__ float lsd_part[kMaxChunk][NW];
@@ -622,12 +625,12 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
       kap -= P;
       ++m;
     }
-    cd z = Y[kap];
+    cd z = (R > 1) ? Yx[kap] : buf[kap];
     if (R > 1) {
       z = cmul(z, wr_s[m]);
       for (int r = 1; r < R; ++r) {
-        const cd t = cmul(Y[r * P + kap], wr_s[r * R + m]);
-        z = cadd(z, t);
+        const cd yv = (r == R - 1) ? buf[kap] : Yx[r * P + kap];
+        z = cadd(z, cmul(yv, wr_s[r * R + m]));
       }
     }
     return z;
@@ -717,10 +720,15 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
 #pragma unroll
         for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b1[144 * q], tw1[q - 1]);
         bfly16<true>(v);
+        cd* Yr = Yx + r * P;
+        if (r == R - 1) {
+          __syncthreads();  // every thread has finished reading buf
+          Yr = buf;
+        }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           const int k = tid + 128 * q;
-          if (k < P) Y[r * P + k] = cmul(v[q], D.post[r * P + k]);
+          if (k < P) Yr[k] = cmul(v[q], D.post[r * P + k]);
         }
       }
       __syncthreads();
@@ -990,7 +998,7 @@ static int v2_min_blocks() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SSR_V2_MIN_BLOCKS");
-    v = (e && e[0] == '2') ? 2 : 3;
+    v = (e && e[0] == '2') ? 2 : ((e && e[0] == '4') ? 4 : 3);
   }
   return v;
 }
@@ -1132,8 +1140,8 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   int grid = sms * per_sm;
   if (grid > w.n_items) grid = w.n_items;
   if (plan->pfa && !force_generic_k1()) {
-    const size_t smem_p = sizeof(cd) * (2048 + 256) + sizeof(cd) * (size_t)plan->n_fft;
-    int gp = sms * 2;
+    const size_t smem_p = sizeof(cd) * (2048 + 256) + sizeof(cd) * (size_t)(plan->n_fft - plan->pdev.P);
+    int gp = sms * 3;
     if (gp > w.n_items) gp = w.n_items;
     const bool store = spec_e || spec_t;
     const bool lsd_only = !store && (flags & 7u) == 1u;
@@ -1188,7 +1196,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
       SSR_CUDA_TRY(cudaEventRecord(ev.first, st));
     }
     const unsigned m3 = flags & 7u;
-    const size_t smem2 = sizeof(cd) * (2048 + 256) + sizeof(float2) * 2048 + sizeof(float) * 2 * 1104;
+    const size_t smem2 = sizeof(cd) * (2048 + 256) + sizeof(float) * 2 * 1104;
     const bool store = spec_e || spec_t;
     const int fixed = (!store && m3 == 1u) ? 1 : ((!store && m3 == 7u) ? 7 : ((spec_e && spec_t && m3 == 7u) ? 15 : -1));
     const int minb = v2_min_blocks();
@@ -1205,6 +1213,11 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
       if (fixed == 1) SSR_V2_LAUNCH(1, 2, 0);
       else if (fixed == 7) SSR_V2_LAUNCH(7, 2, 0);
       else SSR_V2_LAUNCH(-1, 2, 0);
+    } else if (minb == 4) {
+      if (fixed == 1) SSR_V2_LAUNCH(1, 4, 2);
+      else if (fixed == 7) SSR_V2_LAUNCH(7, 3, 2);
+      else if (fixed == 15) SSR_V2_LAUNCH(15, 3, 2);
+      else SSR_V2_LAUNCH(-1, 3, 2);
     } else if (fixed == 1) {
       if (var == 1) SSR_V2_LAUNCH(1, 3, 1);
       else if (var == 2) SSR_V2_LAUNCH(1, 3, 2);

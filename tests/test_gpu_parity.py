@@ -91,23 +91,46 @@ def test_ragged_batch_p2048_vs_oracle(engines):
         assert np.isnan(got[i][3]) == (frames < 7)
 
 
-def test_generic_and_specialised_2048_kernels_agree():
-    """n_fft 2048 normally runs the specialised 16x16x8 kernel; the generic radix-8 kernel (forced
-    through SSR_FORCE_GENERIC_K1 in a subprocess) must give the same metrics."""
+def _run_forced(code, var):
     import json, os, subprocess, sys
+    outs = []
+    for force in ("0", "1"):
+        env = dict(os.environ)
+        env[var] = force
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
+        outs.append(np.array(json.loads(r.stdout.strip().splitlines()[-1])))
+    return outs
+
+
+_ROOT = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (2229, 480), (1114, 240), (743, 160)])
+def test_specialised_and_generic_k1_kernels_agree(n_fft, hop):
+    """n_fft 2048 runs the 16x16x8 kernel and 2229 / 1114 / 743 the PFA kernel; the generic radix-8 /
+    Bluestein kernel (forced through SSR_FORCE_GENERIC_K1 in a subprocess) must give the same metrics."""
     code = (
         "import sys, json, numpy as np; sys.path.insert(0, %r)\n"
         "from ssr_eval_b200.engine import StftMetrics\n"
         "from ssr_eval_b200.synth import speech_like\n"
         "t = speech_like(30000, 48000, seed=5); e = (t + 1e-3*np.random.default_rng(0).standard_normal(30000)).astype(np.float32)\n"
-        "print(json.dumps(StftMetrics(2048, 512).metrics([e, t[:9000]], [t, e[:9000]]).tolist()))\n"
-    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for force in ("0", "1"):
-        env = dict(os.environ, SSR_FORCE_GENERIC_K1=force)
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
-        outs.append(np.array(json.loads(r.stdout.strip().splitlines()[-1])))
-    assert np.abs(outs[0] - outs[1]).max() < 1e-6, outs
+        "print(json.dumps(StftMetrics(%d, %d).metrics([e, t[:9000]], [t, e[:9000]]).tolist()))\n"
+    ) % (_ROOT, n_fft, hop)
+    a, b = _run_forced(code, "SSR_FORCE_GENERIC_K1")
+    assert np.abs(a - b).max() < 1e-6, (a, b)
+
+
+def test_specialised_and_generic_k4_kernels_agree():
+    code = (
+        "import sys, json, numpy as np; sys.path.insert(0, %r)\n"
+        "from ssr_eval_b200.lowpass import stft_hard_lowpass_batch\n"
+        "from ssr_eval_b200.synth import speech_like\n"
+        "w = [speech_like(n, 44100, seed=9 + n %% 5) for n in (30000, 1025, 14113)]\n"
+        "y = stft_hard_lowpass_batch(w, [0.3, 0.9, 0.5])\n"
+        "print(json.dumps(np.concatenate(y).tolist()))\n"
+    ) % _ROOT
+    a, b = _run_forced(code, "SSR_FORCE_GENERIC_K4")
+    assert np.abs(a - b).max() < 5e-6, np.abs(a - b).max()
 
 
 def test_flag_subsets_and_batch_invariance(engines):

@@ -65,7 +65,7 @@ def main():
         off_d = torch.from_numpy(off).to(dev)
         eng = StftMetrics(2229, 480)
         out = torch.empty((n, 4), dtype=torch.float64, device=dev)
-        for flags, name in ((1, "K1 2229/480 (Bluestein M=8192) LSD"), (15, "K1+K2 2229/480 all four")):
+        for flags, name in ((1, "K1 2229/480 (PFA 3x743) LSD"), (15, "K1+K2 2229/480 all four")):
             ms = timeit(lambda: eng.metrics_device(est, tgt, off, flags, offsets_dev=off_d, out=out), iters=3, warm=1)
             report(name, ms, n, "pairs", n * (8 * L + 32))
         del tgt, est
