@@ -122,6 +122,20 @@ int ssr_stft_hard_lowpass_batched(const ssr_lowpass_plan* plan, const float* x_d
                                   const int64_t* offsets_host, const int64_t* offsets_dev, int n,
                                   const int32_t* cut_bins_dev, float* y_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K6 ("next" row): the STFT splice of BasicTestee.postprocessing
+ * (ssr_eval/eval.py:33-41): librosa.stft (n_fft 2048, hop 512) of the model input x and of the model
+ * output, bins below cut_bin taken from x, librosa.istft(length = len(out)).  x and out of a pair
+ * must have the same length (the reference's array assignment requires equal frame counts).
+ * cut_bins_dev: one int32 per utterance = BasicTestee._get_cutoff_index(x) (eval.py:28-31).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssr_splice_plan ssr_splice_plan;
+int ssr_splice_plan_create(ssr_splice_plan** plan, int n_fft, int hop);
+int ssr_splice_plan_destroy(ssr_splice_plan* plan);
+int ssr_stft_splice_istft_batched(const ssr_splice_plan* plan, const float* x_dev, const float* out_dev,
+                                  const int64_t* offsets_host, const int64_t* offsets_dev, int n,
+                                  const int32_t* cut_bins_dev, float* y_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,7 @@ from .metrics import (  # noqa: F401
     EPS, AudioMetricsOracle, lsd, sispec, to_log, energy_unify, pow_norm, pow_p_norm,
     ssim_skimage, evaluation, evaluation_exact_reductions, dict_mean,
 )
+from .postproc import istft, find_cutoff, get_cutoff_index, postprocessing  # noqa: F401
 from .lowpass import (  # noqa: F401
     TorchlibrosaSTFT, TorchlibrosaISTFT, FDomainHelperOracle, stft_hard_lowpass_v0,
     subsampling, align_length, lowpass, librosa_resample_polyphase, resample_poly,

@@ -53,6 +53,9 @@ def lib():
     L.ssr_lowpass_plan_create.argtypes = [ctypes.POINTER(vp), c_int, c_int]
     L.ssr_lowpass_plan_destroy.argtypes = [vp]
     L.ssr_stft_hard_lowpass_batched.argtypes = [vp, vp, vp, vp, c_int, vp, vp, vp]
+    L.ssr_splice_plan_create.argtypes = [ctypes.POINTER(vp), c_int, c_int]
+    L.ssr_splice_plan_destroy.argtypes = [vp]
+    L.ssr_stft_splice_istft_batched.argtypes = [vp, vp, vp, vp, vp, c_int, vp, vp, vp]
     _lib = L
     return L
 
@@ -85,4 +88,5 @@ EXPORTED_SYMBOLS = (
     "ssr_resample_plan_create", "ssr_resample_plan_destroy", "ssr_resample_out_len",
     "ssr_resample_poly_batched",
     "ssr_lowpass_plan_create", "ssr_lowpass_plan_destroy", "ssr_stft_hard_lowpass_batched",
+    "ssr_splice_plan_create", "ssr_splice_plan_destroy", "ssr_stft_splice_istft_batched",
 )

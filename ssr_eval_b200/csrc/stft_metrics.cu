@@ -170,6 +170,11 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+
 struct SyncThreads {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
@@ -829,8 +834,8 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   const bool ok0 = (c0 + c) < cols_out, ok1 = (c0 + c + 1) < cols_out;
   const float* E = spec_e + spec_off[p];
   const float* G = spec_t + spec_off[p];
-  constexpr int RB = kSsimTC + 8;
-  __shared__ __align__(16) float rowbuf[2][2][RB];
+  constexpr int RB = kSsimTC + 8, STAGES = 4;
+  __shared__ __align__(16) float rowbuf[STAGES][2][RB];
   __shared__ double red[kSsimThreads / 32];
 
   float ring[7][10];
@@ -845,36 +850,37 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   const float inv49 = 1.0f / 49.0f, cov_norm = 49.0f / 48.0f;
   const float C1 = 0.0004f, C2 = 0.0036f;  // (0.01*2)^2, (0.03*2)^2
 
-  float pre_e[3], pre_g[3];
-  auto fetch_row = [&](int r) {
-    const float* er = E + (long long)r * F + c0;
-    const float* gr = G + (long long)r * F + c0;
+  // rows stream global -> shared with cp.async (LDGSTS), STAGES-1 rows in flight; columns beyond the
+  // image are zero-filled by the copy itself (src-size 0)
+  auto issue_row = [&](int r) {
+    if (r < r_end) {
+      const int stg = (r - r0) % STAGES;
+      const float* er = E + (long long)r * F + c0;
+      const float* gr = G + (long long)r * F + c0;
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int col = t + u * kSsimThreads;
-      const bool in = (u < 2 || t < 8) && (c0 + col) < F;
-      pre_e[u] = in ? __ldg(er + col) : 0.f;
-      pre_g[u] = in ? __ldg(gr + col) : 0.f;
+      for (int u = 0; u < 3; ++u) {
+        const int col = t + u * kSsimThreads;
+        if (u < 2 || t < 8) {
+          const bool in = (c0 + col) < F;
+          cp_async4(&rowbuf[stg][0][col], in ? er + col : er, in ? 4 : 0);
+          cp_async4(&rowbuf[stg][1][col], in ? gr + col : gr, in ? 4 : 0);
+        }
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  fetch_row(r0);
+#pragma unroll
+  for (int k = 0; k < STAGES - 1; ++k) issue_row(r0 + k);
+
   for (int rb = r0; rb < r_end; rb += 7) {
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
       const int r = rb + s;
       if (r < r_end) {  // uniform across the CTA
-        const int par = (r - r0) & 1;
-        // tile row (kSsimTC + 6 values per image, zero beyond the image) was fetched one row ahead
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const int col = t + u * kSsimThreads;
-          if (u < 2 || t < 8) {
-            rowbuf[par][0][col] = pre_e[u];
-            rowbuf[par][1][col] = pre_g[u];
-          }
-        }
-        __syncthreads();
-        if (r + 1 < r_end) fetch_row(r + 1);
+        const int par = (r - r0) % STAGES;
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+        __syncthreads();               // row r has landed for everyone; row r-1 is fully consumed
+        issue_row(r + STAGES - 1);     // refills the stage row r-1 occupied
         float x[8], y[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -928,6 +934,7 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   double r = warp_sum((double)acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = r;
   __syncthreads();

@@ -260,6 +260,54 @@ class HardLowpass:
         return [y[s:e].copy() for s, e in zip(off[:-1], off[1:])]
 
 
+class SpliceIstft:
+    """K6: the STFT splice + ISTFT of BasicTestee.postprocessing (ssr_eval/eval.py:28-41)."""
+
+    def __init__(self, n_fft=2048, hop=512):
+        _require_cuda()
+        self.n_fft, self.hop = int(n_fft), int(hop)
+        self._plan = ctypes.c_void_p()
+        N.check(N.lib().ssr_splice_plan_create(ctypes.byref(self._plan), self.n_fft, self.hop),
+                "ssr_splice_plan_create")
+        self._stft = StftMetrics(self.n_fft, self.hop)
+
+    def __del__(self):
+        try:
+            if self._plan:
+                N.lib().ssr_splice_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+    def cutoff_indices(self, x_list):
+        """BasicTestee._get_cutoff_index (eval.py:21-31) per utterance: |STFT| summed over the frames,
+        cumulative sum over the bins, last bin whose cumulative energy is below 97 % of the total."""
+        mags = self._stft.magnitude(x_list)
+        out = []
+        for m in mags:
+            energy = np.cumsum(np.sum(np.ascontiguousarray(m.T), axis=-1))  # (F,), as the reference's numpy ops
+            level = energy[-1] * 0.97
+            below = np.nonzero(energy[:0:-1] < level)[0]  # scans x[-1], x[-2], ..., x[1]
+            out.append(int(energy.shape[0] - (below[0] + 1)) if len(below) else 0)
+        return out
+
+    def apply(self, x_list, out_list, cut_bins):
+        assert len(x_list) == len(out_list) == len(cut_bins) and len(x_list) > 0
+        for a, b in zip(x_list, out_list):
+            if len(a) != len(b):
+                raise ValueError("postprocessing: input and output need the same length (%d vs %d)" % (len(a), len(b)))
+        x_h, off = pack_ragged(x_list, pinned=True)
+        o_h, _ = pack_ragged(out_list, pinned=True)
+        x_d, o_d = x_h.cuda(non_blocking=True), o_h.cuda(non_blocking=True)
+        off_d = torch.from_numpy(off).to(x_d.device)
+        cb = torch.as_tensor(np.asarray(cut_bins, dtype=np.int32)).to(x_d.device)
+        y = torch.empty_like(o_d)
+        N.check(N.lib().ssr_stft_splice_istft_batched(self._plan, _ptr(x_d), _ptr(o_d), _np_ptr(off), _ptr(off_d),
+                                                      len(x_list), _ptr(cb), _ptr(y), _stream()),
+                "ssr_stft_splice_istft_batched")
+        yh = y.cpu().numpy()
+        return [yh[s:e].copy() for s, e in zip(off[:-1], off[1:])]
+
+
 class HostPipeline:
     """Host-buffer entry point of K1/K2: (pinned) host batches are streamed to the GPU in chunks on a
     copy stream, double-buffered against the kernels, and the (n, 4) float64 result is read back.

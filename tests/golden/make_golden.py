@@ -31,7 +31,7 @@ def _load_reference():
     pkg.__path__ = [os.path.join(REF, "ssr_eval")]
     sys.modules["ssr_eval"] = pkg
     mods = {}
-    for name in ("utils", "dsp", "metrics", "lowpass"):
+    for name in ("utils", "dsp", "metrics", "lowpass", "eval"):
         spec = importlib.util.spec_from_file_location(
             "ssr_eval." + name, os.path.join(REF, "ssr_eval", name + ".py"))
         m = importlib.util.module_from_spec(spec)
@@ -118,6 +118,17 @@ def main():
     keys = ["lsd", "log_sispec", "sispec", "ssim"]
     spk_means = [dm([dict(zip(keys, row)) for row in a]) for a in per_spk]
     avg = dm(spk_means)
+    # BasicTestee.postprocessing (eval.py:33-41) run by the reference's own class (librosa stft/istft shims)
+    BasicTestee = ref["eval"].BasicTestee
+    xin = lowpass(speech_like(22050, sr=44100, seed=8), 4000, 44100, order=1, _type="stft_hard")
+    model_out = (xin + 0.02 * np.random.default_rng(9).standard_normal(22050)).astype(np.float32)
+    bt = BasicTestee()
+    out["PP/x"] = xin.astype(np.float32)
+    out["PP/out"] = model_out
+    out["PP/cutoff"] = np.int64(bt._get_cutoff_index(xin))
+    out["PP/renewed"] = np.asarray(bt.postprocessing(xin, model_out), dtype=np.float32)
+    print("postprocessing cutoff index", int(out["PP/cutoff"]))
+
     out["AGG/values"] = np.concatenate(per_spk)
     out["AGG/counts"] = np.array([len(a) for a in per_spk])
     out["AGG/averaged"] = np.array([avg[k] for k in keys])

@@ -285,3 +285,26 @@ def test_helper_end_to_end(tmp_path, monkeypatch):
     assert len(list((tmp_path / "results").glob("*-unit.json"))) == 1
     # unprocessed-identity LSD at cutoff 12 kHz lands where the reference's published numbers do (4.5-5.8)
     assert 3.5 < res["averaged"]["proc_fft_24000_44100"]["lsd"] < 7.0
+
+
+def test_postprocessing_golden_and_oracle(golden):
+    """BasicTestee.postprocessing (K6) against the golden produced by the reference's own class and
+    against the oracle on a second, ragged case.  float32 output of a float64 STFT/ISTFT: <= 2e-6 abs."""
+    from ssr_eval_b200 import BasicTestee
+    from ssr_eval_b200.engine import SpliceIstft
+    x, out = golden["PP/x"], golden["PP/out"]
+    bt = BasicTestee()
+    assert bt._get_cutoff_index(x) == int(golden["PP/cutoff"])
+    y = bt.postprocessing(x, out)
+    assert y.shape == out.shape and y.dtype == np.float32
+    assert np.abs(y - golden["PP/renewed"]).max() <= 2e-6
+    eng = SpliceIstft()
+    xs = [oracle.lowpass(speech_like(n, 44100, seed=90 + i), c, 44100, order=1, _type="stft_hard").astype(np.float32)
+          for i, (n, c) in enumerate(((30000, 8000), (1025, 4000), (16385, 12000)))]
+    outs = [(a + 0.01 * np.random.default_rng(i).standard_normal(len(a))).astype(np.float32) for i, a in enumerate(xs)]
+    cuts = eng.cutoff_indices(xs)
+    assert cuts == [oracle.get_cutoff_index(a) for a in xs]
+    got = eng.apply(xs, outs, cuts)
+    for a, o, g in zip(xs, outs, got):
+        want = oracle.postprocessing(a, o)
+        assert np.abs(g - want).max() <= 2e-6, (len(a), np.abs(g - want).max())
