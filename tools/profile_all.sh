@@ -2,7 +2,7 @@
 # Round-end profiling pass (run under gpurun, 1 GPU).  Outputs land in gpurun_out/.
 set -x
 # 1. launch list of the contract bench command (cold-cache, serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/bench_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/bench_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 # 2. full-set captures, one launch per kernel
 ncu --set full --clock-control none --import-source on -k regex:k_stft_metrics_2048 -s 3 -c 1 -o gpurun_out/prof_k1_final \
