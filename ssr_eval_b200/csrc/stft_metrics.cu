@@ -152,20 +152,6 @@ __device__ __forceinline__ float __fsqrt_approx(float x) {
   return r;
 }
 
-// exact float32 -> float64 for normal inputs with four ALU-pipe integer ops (no XU F2F):
-// hi = ((bits asr 3) & 0x8FFFFFFF) + 0x38000000, lo = bits << 29.  Zero / denormal inputs map to
-// +-2^-127-scale values instead of themselves, 26 orders of magnitude below the 1e-12 floors of the
-// metric formulas.
-__device__ __forceinline__ double f2d_bits(float x) {
-  const int b = __float_as_int(x);
-  const int hi = ((b >> 3) & (int)0x8FFFFFFF) + 0x38000000;
-  const int lo = b << 29;
-  return __hiloint2double(hi, lo);
-}
-template <int VAR>
-__device__ __forceinline__ double f2d(float x) {
-  return (VAR & 1) ? f2d_bits(x) : (double)x;
-}
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
@@ -344,10 +330,8 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
 // FIXED >= 0: the metric flags are the compile-time constant FIXED (bit 3 = the magnitude
 // spectrograms are written for K2); hot configurations: 1 = LSD only, 7 = LSD + log-sispec + sispec,
 // 15 = those + spectrograms.  FIXED < 0: run-time flags.
-// VAR: experimental variants (bit 0: float->double input conversion with integer ops on the ALU
-// pipe instead of F2F on the XU pipe; bit 1: L1 prefetch of the next frame's new samples).
-template <int FIXED, int MINB, int VAR>
-__global__ void __launch_bounds__(kV2Threads, MINB)
+template <int FIXED>
+__global__ void __launch_bounds__(kV2Threads, 3)
 k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __restrict__ tgt,
                     const long long* __restrict__ offsets, const int* __restrict__ item_start,
                     const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
@@ -416,9 +400,9 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const double w = __ldg(P.win_half + tid + 128 * r);
-          v[r] = cd{w * f2d<VAR>(__ldg(pt + 128 * r)), w * f2d<VAR>(__ldg(pe + 128 * r))};
+          v[r] = cd{w * (double)__ldg(pt + 128 * r), w * (double)__ldg(pe + 128 * r)};
         }
-        if ((VAR & 2) && tid < 32) {
+        if (tid < 32) {
           // next frame's new samples: [start + N, start + N + hop) of both signals, one 128 B line per lane
           const long long nxt = start + N + (long long)(tid & 15) * 32;
           if (nxt < L && (tid & 15) * 32 < hop) prefetch_l1((tid < 16 ? xt : xe) + nxt);
@@ -1000,25 +984,6 @@ static bool force_generic_k1() {
   return v == 1;
 }
 
-// resident CTAs per SM the 2048 kernel is compiled for (register cap 168 at 3, 255 at 2)
-static int v2_min_blocks() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SSR_V2_MIN_BLOCKS");
-    v = (e && e[0] == '2') ? 2 : ((e && e[0] == '4') ? 4 : 3);
-  }
-  return v;
-}
-
-static int v2_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SSR_V2_VARIANT");
-    v = e ? atoi(e) : 2;
-  }
-  return v;
-}
-
 struct WsLayout {
   size_t item_start, item_pair, spec_off, partials, ssim_part, spec_e, spec_t, total;
   int chunk, n_items, tiles_x, tiles_per_pair;
@@ -1206,35 +1171,18 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     const size_t smem2 = sizeof(cd) * (2048 + 256) + sizeof(float) * 2 * 1104;
     const bool store = spec_e || spec_t;
     const int fixed = (!store && m3 == 1u) ? 1 : ((!store && m3 == 7u) ? 7 : ((spec_e && spec_t && m3 == 7u) ? 15 : -1));
-    const int minb = v2_min_blocks();
-    if (g2 > sms * minb) g2 = sms * minb;
-#define SSR_V2_LAUNCH(FX, MB, VR)                                                                      \
+    if (g2 > sms * 3) g2 = sms * 3;
+#define SSR_V2_LAUNCH(FX)                                                                           \
   do {                                                                                              \
-    auto kern = k_stft_metrics_2048<FX, MB, VR>;                                                       \
+    auto kern = k_stft_metrics_2048<FX>;                                                            \
     SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
     kern<<<g2, kV2Threads, smem2, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
                                         w.chunk, flags, partials, spec_e, spec_t, spec_off);        \
   } while (0)
-    const int var = v2_variant();
-    if (minb == 2) {
-      if (fixed == 1) SSR_V2_LAUNCH(1, 2, 0);
-      else if (fixed == 7) SSR_V2_LAUNCH(7, 2, 0);
-      else SSR_V2_LAUNCH(-1, 2, 0);
-    } else if (minb == 4) {
-      if (fixed == 1) SSR_V2_LAUNCH(1, 4, 2);
-      else if (fixed == 7) SSR_V2_LAUNCH(7, 3, 2);
-      else if (fixed == 15) SSR_V2_LAUNCH(15, 3, 2);
-      else SSR_V2_LAUNCH(-1, 3, 2);
-    } else if (fixed == 1) {
-      if (var == 1) SSR_V2_LAUNCH(1, 3, 1);
-      else if (var == 2) SSR_V2_LAUNCH(1, 3, 2);
-      else if (var == 3) SSR_V2_LAUNCH(1, 3, 3);
-      else SSR_V2_LAUNCH(1, 3, 0);
-    } else {
-      if (fixed == 7) SSR_V2_LAUNCH(7, 3, 2);
-      else if (fixed == 15) SSR_V2_LAUNCH(15, 3, 2);
-      else SSR_V2_LAUNCH(-1, 3, 2);
-    }
+    if (fixed == 1) SSR_V2_LAUNCH(1);
+    else if (fixed == 7) SSR_V2_LAUNCH(7);
+    else if (fixed == 15) SSR_V2_LAUNCH(15);
+    else SSR_V2_LAUNCH(-1);
 #undef SSR_V2_LAUNCH
     SSR_LAUNCH_CHECK("k_stft_metrics_2048");
     if (tm.on) {

@@ -308,3 +308,52 @@ def test_postprocessing_golden_and_oracle(golden):
     for a, o, g in zip(xs, outs, got):
         want = oracle.postprocessing(a, o)
         assert np.abs(g - want).max() <= 2e-6, (len(a), np.abs(g - want).max())
+
+
+def test_many_small_utterances_cross_launch_chunks(engines):
+    """> 32768 utterances in one call: the launch-chunking loops of K2 / K3 / K4 (gridDim.y limit)."""
+    from ssr_eval_b200.engine import PolyphaseResampler, HardLowpass
+    n = 33000
+    base = [speech_like(3600 + 7 * i, sr=16000, seed=200 + i) for i in range(4)]
+    waves = [base[i % 4] for i in range(n)]
+    # K3
+    ys = PolyphaseResampler(3, 2).resample(waves)
+    for i in (0, 1, 2, 3, 32767, 32768, n - 1):
+        assert np.array_equal(ys[i], resample_poly(waves[i], 3, 2))
+    # K4
+    lp = HardLowpass(2048, 441)
+    zs = lp.apply(waves, [0.25 + 0.1 * (i % 4) for i in range(n)])
+    for i in (0, 5, 32767, 32768, n - 1):
+        want = oracle.stft_hard_lowpass_v0(waves[i], 0.25 + 0.1 * (i % 4))
+        assert np.abs(zs[i] - want).max() <= 2e-5
+    # K1 + K2 (n_fft 743 / hop 160 -> >= 7 frames at these lengths)
+    est = [(w * 0.8 + 0.01 * np.random.default_rng(i).standard_normal(len(w))).astype(np.float32)
+           for i, w in enumerate(base)]
+    got = engines(743, 160).metrics([est[i % 4] for i in range(n)], waves)
+    ref = engines(743, 160).metrics(est, base)
+    for i in (0, 1, 2, 3, 32767, 32768, 32769, n - 1):
+        assert np.array_equal(got[i], ref[i % 4]), i
+
+
+def test_helper_subsampling_and_iir_settings(tmp_path, monkeypatch):
+    """setting_subsampling (K3 twice) and setting_lowpass_filtering (scipy passthrough) through the helper:
+    key naming of eval.py:334-421 and parity of the degraded inputs with the oracle."""
+    from scipy.io import wavfile
+    from ssr_eval_b200 import SSR_Eval_Helper, BasicTestee
+    root = tmp_path / "vctk"
+    (root / "p1").mkdir(parents=True)
+    x = speech_like(22050, 44100, seed=77)
+    wavfile.write(str(root / "p1" / "a.wav"), 44100, x)
+    monkeypatch.chdir(tmp_path)
+    h = SSR_Eval_Helper(BasicTestee(), input_sr=44100, output_sr=44100, evaluation_sr=44100, test_name="unit2",
+                        test_data_root=str(root), setting_subsampling={"cutoff_freq": [8000]},
+                        setting_lowpass_filtering={"filter": ["butter", "cheby"], "cutoff_freq": [6000], "filter_order": [4]})
+    d = h.preprocess(str(root / "p1" / "a.wav"), 44100)
+    assert list(d) == ["proc_bw_12000_4_44100", "proc_ch_12000_4_44100", "proc_subsampling_16000_44100"]
+    assert np.array_equal(d["proc_subsampling_16000_44100"], oracle.lowpass(x, 8000, 44100, order=1, _type="subsampling"))
+    np.testing.assert_allclose(d["proc_bw_12000_4_44100"], oracle.lowpass(x, 6000, 44100, order=4, _type="butter"))
+    res = h.evaluate()
+    assert set(res["averaged"]) == set(d)
+    for k in d:
+        want = oracle.evaluation(d[k].astype(np.float32), x, rate=44100)
+        _assert_metrics(res["p1"]["a.wav"][k], want, k)
