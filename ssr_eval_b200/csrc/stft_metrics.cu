@@ -565,8 +565,12 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
 // than the generic Bluestein kernel).  NQ = ceil(P / 128): pass-1 inputs / pass-3' outputs beyond
 // NQ are structurally zero / unused and are pruned at compile time.
 // ---------------------------------------------------------------------------------------------
-template <int NQ, int FIXED>
-__global__ void __launch_bounds__(kV2Threads, 3)
+// PIPE = 1: 2 CTAs/SM (255 registers): the Bluestein filter values of the thread's two butterflies
+// live in registers and the samples + window*chirp factors of the NEXT sub-transform are fetched into
+// registers one sub-transform ahead (the tables do not fit the L1 left beside 3 CTAs' shared memory,
+// so every table load is an L2 round trip that has to be hidden in software).
+template <int NQ, int FIXED, int PIPE>
+__global__ void __launch_bounds__(kV2Threads, PIPE ? 2 : 3)
 k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restrict__ tgt,
                    const long long* __restrict__ offsets, const int* __restrict__ item_start,
                    const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
@@ -608,6 +612,15 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
   const cd* const t2 = tw2 + j2;
   __syncthreads();
 
+  cd fa[8], fb[8];  // PIPE: Bluestein filter at this thread's 16 slots
+  if (PIPE) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      fa[q] = D.bfilt[8 * ia + q];
+      fb[q] = D.bfilt[8 * ib + q];
+    }
+  }
+
   auto combine = [&](int kap) {  // Z[kap] = sum_r W_R^{r m} Y_r[k], kap = k + P m
     int m = 0;
     while (kap >= P) {
@@ -637,6 +650,29 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
     const float* xt = tgt + off;
     double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
 
+    // (PIPE) inputs of sub-transform (f, r): samples of both signals and window*chirp, NQ per thread
+    float ptx[NQ], pex[NQ];
+    cd pcw[NQ];
+    auto fetch_inputs = [&](long long f, int r) {
+      const long long start = f * hop - N / 2;
+      const bool interior = (start >= 0 && start + N <= L);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int n = tid + 128 * q;
+        ptx[q] = 0.f;
+        pex[q] = 0.f;
+        pcw[q] = cd{0.0, 0.0};
+        if (n < P) {
+          const long long si = start + (long long)R * n + r;
+          const long long idx = interior ? si : reflect_index(si, L);
+          ptx[q] = __ldg(xt + idx);
+          pex[q] = __ldg(xe + idx);
+          pcw[q] = D.cwin[r * P + n];
+        }
+      }
+    };
+    if (PIPE) fetch_inputs(f0, 0);
+
     for (int fi = 0; fi < nf; ++fi) {
       const long long f = f0 + fi;
       const long long start = f * hop - N / 2;
@@ -644,17 +680,31 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
       for (int r = 0; r < R; ++r) {
         cd v[16];
         // ---- forward pass 1: a[n] = z[R n + r] * (0.5 window * chirp), zero padded to 2048
+        if (PIPE) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          v[q] = cd{0.0, 0.0};
-          if (q < NQ) {
-            const int n = tid + 128 * q;
-            if (n < P) {
-              const long long si = start + (long long)R * n + r;
-              const long long idx = interior ? si : reflect_index(si, L);
-              const double tt = (double)__ldg(xt + idx), ee = (double)__ldg(xe + idx);
-              const cd w = D.cwin[r * P + n];
-              v[q] = cd{tt * w.x - ee * w.y, tt * w.y + ee * w.x};
+          for (int q = 0; q < 16; ++q) {
+            v[q] = cd{0.0, 0.0};
+            if (q < NQ) {
+              const double tt = (double)ptx[q], ee = (double)pex[q];
+              v[q] = cd{tt * pcw[q].x - ee * pcw[q].y, tt * pcw[q].y + ee * pcw[q].x};
+            }
+          }
+          // the loads of the next sub-transform fly during all passes of this one
+          if (r + 1 < R) fetch_inputs(f, r + 1);
+          else if (fi + 1 < nf) fetch_inputs(f + 1, 0);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            v[q] = cd{0.0, 0.0};
+            if (q < NQ) {
+              const int n = tid + 128 * q;
+              if (n < P) {
+                const long long si = start + (long long)R * n + r;
+                const long long idx = interior ? si : reflect_index(si, L);
+                const double tt = (double)__ldg(xt + idx), ee = (double)__ldg(xe + idx);
+                const cd w = D.cwin[r * P + n];
+                v[q] = cd{tt * w.x - ee * w.y, tt * w.y + ee * w.x};
+              }
             }
           }
         }
@@ -685,8 +735,8 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
         bfly8<false>(b);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          a[q] = cmul(a[q], D.bfilt[8 * ia + q]);
-          b[q] = cmul(b[q], D.bfilt[8 * ib + q]);
+          a[q] = cmul(a[q], PIPE ? fa[q] : D.bfilt[8 * ia + q]);
+          b[q] = cmul(b[q], PIPE ? fb[q] : D.bfilt[8 * ib + q]);
         }
         bfly8<true>(a);
         bfly8<true>(b);
@@ -984,6 +1034,16 @@ static bool force_generic_k1() {
   return v == 1;
 }
 
+// SSR_PFA_PIPE=0/1: PFA kernel without / with software-pipelined inputs (A/B tests)
+static int pfa_pipe() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_PFA_PIPE");
+    v = e ? atoi(e) : 1;
+  }
+  return v ? 1 : 0;
+}
+
 struct WsLayout {
   size_t item_start, item_pair, spec_off, partials, ssim_part, spec_e, spec_t, total;
   int chunk, n_items, tiles_x, tiles_per_pair;
@@ -1113,7 +1173,8 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   if (grid > w.n_items) grid = w.n_items;
   if (plan->pfa && !force_generic_k1()) {
     const size_t smem_p = sizeof(cd) * (2048 + 256) + sizeof(cd) * (size_t)(plan->n_fft - plan->pdev.P);
-    int gp = sms * 3;
+    const int pipe = pfa_pipe();
+    int gp = sms * (pipe ? 2 : 3);
     if (gp > w.n_items) gp = w.n_items;
     const bool store = spec_e || spec_t;
     const bool lsd_only = !store && (flags & 7u) == 1u;
@@ -1132,7 +1193,12 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     }
 #define SSR_PFA_LAUNCH(NQ_, FX)                                                                      \
   do {                                                                                               \
-    auto kern = k_stft_metrics_pfa<NQ_, FX>;                                                         \
+    if (pipe) SSR_PFA_LAUNCH_(NQ_, FX, 1);                                                           \
+    else SSR_PFA_LAUNCH_(NQ_, FX, 0);                                                                \
+  } while (0)
+#define SSR_PFA_LAUNCH_(NQ_, FX, PP)                                                                 \
+  do {                                                                                               \
+    auto kern = k_stft_metrics_pfa<NQ_, FX, PP>;                                                     \
     SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
     kern<<<gp, kV2Threads, smem_p, st>>>(plan->pdev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
                                          w.chunk, flags, partials, spec_e, spec_t, spec_off);        \
@@ -1145,6 +1211,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
       else SSR_PFA_LAUNCH(8, -1);
     }
 #undef SSR_PFA_LAUNCH
+#undef SSR_PFA_LAUNCH_
     SSR_LAUNCH_CHECK("k_stft_metrics_pfa");
     if (tm.on) {
       SSR_CUDA_TRY(cudaEventRecord(ev.second, st));

@@ -331,8 +331,10 @@ def test_many_small_utterances_cross_launch_chunks(engines):
            for i, w in enumerate(base)]
     got = engines(743, 160).metrics([est[i % 4] for i in range(n)], waves)
     ref = engines(743, 160).metrics(est, base)
+    # the frames-per-work-item chunk grows with the batch, which regroups the float64 partial sums:
+    # values agree to rounding (1e-12), and are bit-identical for equal chunking (test above)
     for i in (0, 1, 2, 3, 32767, 32768, 32769, n - 1):
-        assert np.array_equal(got[i], ref[i % 4]), i
+        np.testing.assert_allclose(got[i], ref[i % 4], rtol=1e-11, atol=1e-12)
 
 
 def test_helper_subsampling_and_iir_settings(tmp_path, monkeypatch):
