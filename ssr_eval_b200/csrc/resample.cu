@@ -75,26 +75,45 @@ k_resample_tiled(const float* __restrict__ x, const long long* __restrict__ in_o
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) h[k] = (k < K) ? __ldg(bank + phase * K + k) : 0.f;
   const long long step = (long long)(TP / up) * down;  // input advance per TP outputs (TP % up == 0)
+  // G outputs are accumulated together: G independent float32 add chains and G*K loads in flight
+  constexpr int G = 4;
+  static_assert(R % G == 0, "R must be a multiple of G");
 #pragma unroll 1
-  for (int i = 0; i < R; ++i) {
-    const long long j = j0 + (long long)i * TP;
-    if (j < n_out) {
-      float acc = 0.f;
-      if (i_hi - (K - 1) >= 0 && i_hi < n_in) {  // interior: no bounds checks
-        const float* px = xu + i_hi;
+  for (int i0 = 0; i0 < R; i0 += G) {
+    float acc[G];
+    bool inner[G], live[G];
+    const float* px[G];
 #pragma unroll
-        for (int k = KMAX - 1; k >= 0; --k)
-          if (k < K) acc = __fadd_rn(acc, __fmul_rn(__ldg(px - k), h[k]));
-      } else {
+    for (int g = 0; g < G; ++g) {
+      const long long ih = i_hi + (long long)g * step;
+      acc[g] = 0.f;
+      live[g] = (j0 + (long long)(i0 + g) * TP) < n_out;
+      inner[g] = live[g] && ih - (K - 1) >= 0 && ih < n_in;
+      px[g] = xu + ih;
+    }
+    if (inner[0] && inner[1] && inner[2] && inner[3]) {  // interior: no bounds checks
+#pragma unroll
+      for (int k = KMAX - 1; k >= 0; --k)
+        if (k < K) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) acc[g] = __fadd_rn(acc[g], __fmul_rn(__ldg(px[g] - k), h[k]));
+        }
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (!live[g]) continue;
+        const long long ih = i_hi + (long long)g * step;
 #pragma unroll
         for (int k = KMAX - 1; k >= 0; --k) {
-          const long long ii = i_hi - k;
-          if (k < K && ii >= 0 && ii < n_in) acc = __fadd_rn(acc, __fmul_rn(__ldg(xu + ii), h[k]));
+          const long long ii = ih - k;
+          if (k < K && ii >= 0 && ii < n_in) acc[g] = __fadd_rn(acc[g], __fmul_rn(__ldg(xu + ii), h[k]));
         }
       }
-      yu[j] = acc;
     }
-    i_hi += step;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (live[g]) yu[j0 + (long long)(i0 + g) * TP] = acc[g];
+    i_hi += (long long)G * step;
   }
 }
 

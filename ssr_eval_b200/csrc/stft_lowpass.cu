@@ -239,16 +239,23 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
         v[r] = cf{w * __ldg(p0 + 128 * r), two ? w * __ldg(p1 + 128 * r) : 0.f};
       }
     } else {
+      // edge frame pair (reflect padding): gather through the FFT buffer (free here: the previous
+      // pair's inverse-pass-3 loads were followed by two barriers) to keep 64-bit reflect math out of
+      // the unrolled path
 #pragma unroll 1
+      for (int n = tid; n < N; n += kV2Threads) {
+        const float a = __ldg(xu + lp_reflect(s0 + n, L));
+        const float b = two ? __ldg(xu + lp_reflect(s1 + n, L)) : 0.f;
+        buf[n] = cf{a, b};
+      }
+      __syncthreads();
+#pragma unroll
       for (int r = 0; r < 16; ++r) {
         const float w = __ldg(P.win + tid + 128 * r);
-        const float a = w * __ldg(xu + lp_reflect(s0 + tid + 128 * r, L));
-        const float b = two ? w * __ldg(xu + lp_reflect(s1 + tid + 128 * r, L)) : 0.f;
-        // dynamic register index is avoided by a select chain on the unrolled copy below
-#pragma unroll
-        for (int rr = 0; rr < 16; ++rr)
-          if (rr == r) v[rr] = cf{a, b};
+        const cf raw = buf[tid + 128 * r];
+        v[r] = cf{w * raw.x, w * raw.y};
       }
+      __syncthreads();  // all raw values are in registers before pass 1 overwrites the buffer
     }
     bfly16<false>(v);
     b1[0] = v[0];
@@ -324,18 +331,19 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
 #pragma unroll
     for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b1[136 * q], tw1[q - 1]);
     bfly16<true>(v);
-    // ---- overlap-add, frame f then frame f+1
+    // ---- overlap-add, frame f then frame f+1 (32-bit indices relative to the item's first sample)
+    const int o0 = (int)(f * hop - m0) + tid;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-      const long long m = f * hop + tid + 128 * r;
-      if (m >= m0 && m < m1) acc[m - m0] += wn[r] * v[r].x;
+      const int i = o0 + 128 * r;
+      if ((unsigned)i < (unsigned)span) acc[i] += wn[r] * v[r].x;
     }
     __syncthreads();
     if (two) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        const long long m = (f + 1) * hop + tid + 128 * r;
-        if (m >= m0 && m < m1) acc[m - m0] += wn[r] * v[r].y;
+        const int i = o0 + hop + 128 * r;
+        if ((unsigned)i < (unsigned)span) acc[i] += wn[r] * v[r].y;
       }
     }
     __syncthreads();
