@@ -74,13 +74,34 @@ def _cpu_work(n):
     return acc
 
 
+def usable_cores():
+    """Host threads this process may actually use: the affinity mask, capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    env = os.environ.get("SSR_BENCH_CPU_CORES")
+    return int(env) if env else n
+
+
 class CpuArm:
     """Persistent process pool, one worker per host core, each running the oracle's
     STFT(float64 pocketfft)+LSD(torch float32) on 5 s pairs."""
 
     def __init__(self, cores=None):
         import multiprocessing as mp
-        self.cores = cores or os.cpu_count() or 1
+        self.cores = cores or usable_cores()
         ctx = mp.get_context("spawn")
         self.pool = ctx.Pool(self.cores, initializer=_cpu_init, initargs=(ctx.Barrier(self.cores),))
         self.pool.map(_cpu_warm, range(self.cores), chunksize=1)  # imports + caches warm in EVERY worker
