@@ -253,6 +253,7 @@ def run_gpu(args):
     out = torch.empty((n_pairs, 4), dtype=torch.float64, device=dev)
     flags = N.METRIC_LSD
     acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    count_t = torch.full((1,), float(n_pairs), dtype=torch.float64, device=dev)
     pending = []
 
     def step():
@@ -260,7 +261,7 @@ def run_gpu(args):
         if world > 1:
             # the single all-reduce of the scalar metric accumulators (sum of LSD, pair count) over
             # NCCL; enqueued asynchronously so ranks are not lock-stepped, completed inside the timed region
-            a = torch.stack((out[:, 0].sum(), out.new_tensor(float(n_pairs))))
+            a = torch.cat((out[:, 0].sum(dim=0, keepdim=True), count_t))
             pending.append((a, td.all_reduce(a, async_op=True)))
 
     def drain():
