@@ -7,7 +7,7 @@ OBJ := build/obj
 LIB := ssr_eval_b200/lib/libssr_b200.so
 SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu $(SRC)/stft_splice.cu
 OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(SRCS))
-HDRS := $(SRC)/common.cuh $(SRC)/fft_core.cuh $(SRC)/stft_tables.hpp $(SRC)/k1_map.cuh include/ssr_b200.h
+HDRS := $(wildcard $(SRC)/*.cuh) $(SRC)/stft_tables.hpp include/ssr_b200.h
 
 all: $(LIB)
 

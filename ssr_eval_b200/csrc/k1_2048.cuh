@@ -1,0 +1,249 @@
+// k1_2048.cuh -- K1, specialised n_fft = 2048 kernel (radix 16x16x8, register-paired epilogue).
+#pragma once
+#include "k1_common.cuh"
+#include "k1_map.cuh"
+
+namespace ssr {
+
+// ---------------------------------------------------------------------------------------------
+// K1, specialised: n_fft = 2048 (BASELINE config 2 and every evaluation at 44.1 kHz).
+// 128 threads, 16 points per thread: radix 16 x 16 x 8 in-place DIF.
+//   pass 1: samples come straight from global memory (coalesced, window folded in), the 15
+//           pass-1 twiddles of a thread never change and live in registers for the CTA's lifetime;
+//   pass 2: twiddles W_128^{jq} (120 values) from a conflict-free shared table;
+//   pass 3: no twiddles; every thread transforms a butterfly AND its Hermitian partner
+//           (k1_map.cuh), so Z[k] and Z[N-k] meet in registers and the epilogue needs no
+//           further shared-memory traffic.
+// Shared-memory traffic per frame: 2 exchanges (4 x 32 KB) + 30 KB of twiddles.
+// ---------------------------------------------------------------------------------------------
+// FIXED >= 0: the metric flags are the compile-time constant FIXED (bit 3 = the magnitude
+// spectrograms are written for K2); hot configurations: 1 = LSD only, 7 = LSD + log-sispec + sispec,
+// 15 = those + spectrograms.  FIXED < 0: run-time flags.
+template <int FIXED>
+__global__ void __launch_bounds__(kV2Threads, 3)
+k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __restrict__ tgt,
+                    const long long* __restrict__ offsets, const int* __restrict__ item_start,
+                    const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
+                    double* __restrict__ partials, float* __restrict__ spec_e,
+                    float* __restrict__ spec_t, const long long* __restrict__ spec_off) {
+  constexpr int N = 2048, F = 1025, NW = kV2Threads / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* const buf = reinterpret_cast<cd*>(smem_raw);                                // N + N/8 slots
+  float2* const edge_raw = reinterpret_cast<float2*>(smem_raw);  // edge frames stage N raw pairs inside buf
+  float* const row_t = reinterpret_cast<float*>(smem_raw + sizeof(cd) * (N + N / 8));  // magnitude rows (store mode)
+  float* const row_e = row_t + 1104;
+  __shared__ __align__(16) cd tw2[15 * 8];
+  __shared__ float lsd_part[kMaxChunk][NW];
+  __shared__ double red[NW][kPartials];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hop = P.hop;
+  if (FIXED >= 0) flags = (unsigned)FIXED;
+  const bool want_lsd = flags & SSR_METRIC_LSD, want_log = flags & SSR_METRIC_LOG_SISPEC,
+             want_lin = flags & SSR_METRIC_SISPEC;
+  if (FIXED >= 0 && !(FIXED & 8)) {
+    spec_e = nullptr;
+    spec_t = nullptr;
+  }
+
+  // per-thread constants
+  cd tw1[15];
+#pragma unroll
+  for (int q = 1; q < 16; ++q) tw1[q - 1] = P.tw[tid * q];
+  if (tid < 120) tw2[tid] = P.tw[16 * (tid & 7) * ((tid >> 3) + 1)];  // tw2[(q-1)*8 + j] = W_128^{jq}
+  int ia, ib;
+  v2_thread_butterflies(tid, &ia, &ib);
+  const bool special = (tid == kV2Threads - 1);
+  const int ka = v2_klow(ia), kb = v2_klow(ib);
+  const int j2 = tid & 7;
+  // padded slots: pass 1 element q -> p1 + 144 q; pass 2 element r -> p2 + 9 r; pass 3 -> 9 i + r
+  cd* const b1 = buf + pad_idx(tid);
+  cd* const b2 = buf + pad_idx((tid >> 3) * 128 + j2);
+  const cd* const b3a = buf + 9 * ia;
+  const cd* const b3b = buf + 9 * ib;
+  const cd* const t2 = tw2 + j2;
+  __syncthreads();
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int p = item_pair[item];
+    const int c = item - item_start[p];
+    const long long off = offsets[p];
+    const long long L = offsets[p + 1] - off;
+    const long long T = stft_frames(L, N, hop);
+    const long long f0 = (long long)c * chunk;
+    const int nf = (int)min((long long)chunk, T - f0);
+    const float* xe = est + off;
+    const float* xt = tgt + off;
+    double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
+    float* pend_t = nullptr;
+    float* pend_e = nullptr;
+
+    for (int fi = 0; fi < nf; ++fi) {
+      const long long f = f0 + fi;
+      const long long start = f * hop - N / 2;
+      cd v[16];
+      // ---- pass 1: load + window, radix-16, twiddle, store
+      if (start >= 0 && start + N <= L) {
+        const float* pt = xt + start + tid;
+        const float* pe = xe + start + tid;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const double w = __ldg(P.win_half + tid + 128 * r);
+          v[r] = cd{w * (double)__ldg(pt + 128 * r), w * (double)__ldg(pe + 128 * r)};
+        }
+        if (tid < 32) {
+          // next frame's new samples: [start + N, start + N + hop) of both signals, one 128 B line per lane
+          const long long nxt = start + N + (long long)(tid & 15) * 32;
+          if (nxt < L && (tid & 15) * 32 < hop) prefetch_l1((tid < 16 ? xt : xe) + nxt);
+        }
+      } else {
+        // edge frame (reflect padding; < 1 % of the frames): gather through a small staging array so
+        // the 64-bit reflect arithmetic stays out of the unrolled hot path
+        __syncthreads();  // the staging area aliases buf: the previous frame's pass-3 loads must be done
+#pragma unroll 1
+        for (int n = tid; n < N; n += kV2Threads) {
+          const long long idx = reflect_index(start + n, L);
+          edge_raw[n] = make_float2(__ldg(xt + idx), __ldg(xe + idx));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const double w = __ldg(P.win_half + tid + 128 * r);
+          const float2 x = edge_raw[tid + 128 * r];
+          v[r] = cd{w * (double)x.x, w * (double)x.y};
+        }
+      }
+      bfly16<false>(v);
+#pragma unroll
+      for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw1[q - 1]);
+      // the previous frame's pass-3 loads must be done before buf is overwritten; placed here (after
+      // this frame's loads and butterfly) the barrier finds every warp long past that point
+      __syncthreads();
+      if (pend_t) {  // coalesced copy-out of the previous frame's magnitude rows (all epilogues are done)
+        for (int k = tid; k < F; k += kV2Threads) {
+          pend_t[k] = row_t[k + (k >> 4)];
+          if (pend_e) pend_e[k] = row_e[k + (k >> 4)];
+        }
+        pend_t = nullptr;
+      }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
+      __syncthreads();
+      // ---- pass 2: sub-transforms of length 128 (stride 8)
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = b2[9 * r];
+      bfly16<false>(v);
+      b2[0] = v[0];
+#pragma unroll
+      for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
+      __syncthreads();
+      // ---- pass 3: two radix-8 butterflies (a and its Hermitian partner b), no twiddles
+      cd* a = v;
+      cd* b = v + 8;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        a[r] = b3a[r];
+        b[r] = b3b[r];
+      }
+      bfly8<false>(a);
+      bfly8<false>(b);
+      // ---- epilogue, from registers
+      float lsd_acc = 0.f;
+      float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
+      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
+      auto emit = [&](int k, cd zk, cd zn) {
+        // T = (Z[k] + conj Z[N-k]) / 2,  E = (Z[k] - conj Z[N-k]) / (2i); the 1/2 is in the window.
+        // complex64 rounding as librosa stores it, then float32 arithmetic as torch runs it; the
+        // special functions are the hardware approximations (MUFU sqrt / rcp / lg2, <= 2 ulp), well
+        // inside the differences that already exist between numpy's hypotf / torch's log10 and any
+        // other libm (SSR_EXACT_F32_EPILOGUE switches to the IEEE-rounded forms for A/B tests).
+        const float tre = (float)(zk.x + zn.x), tim = (float)(zk.y - zn.y);
+        const float ere = (float)(zk.y + zn.y), eim = (float)(zn.x - zk.x);
+        const float tx = tre * tre + tim * tim;  // |T|^2
+        const float ey = ere * ere + eim * eim;  // |E|^2
+#ifdef SSR_EXACT_F32_EPILOGUE
+        const float mt = sqrtf(tx), me = sqrtf(ey);
+#else
+        const float me = __fsqrt_approx(ey);
+        const float mt = (st || want_lin || want_log) ? __fsqrt_approx(tx) : 0.f;
+#endif
+        if (st) {  // staged through shared memory (slot k + k/16: conflict-free for the scattered k of a warp)
+          row_t[k + (k >> 4)] = mt;
+          row_e[k + (k >> 4)] = me;
+        }
+        if (want_lsd) {
+          const float den = me + 1e-12f;
+#ifdef SSR_EXACT_F32_EPILOGUE
+          const float l = log10f((mt * mt) / (den * den) + 1e-12f);
+#else
+          const float l = __log10f(__fdividef(tx, den * den) + 1e-12f);
+#endif
+          lsd_acc += l * l;
+        }
+        if (want_lin) {
+          const double de = (double)me, dt = (double)mt;
+          s_et = fma(de, dt, s_et);
+          s_tt = fma(dt, dt, s_tt);
+          s_ee = fma(de, de, s_ee);
+        }
+        if (want_log) {
+#ifdef SSR_EXACT_F32_EPILOGUE
+          const double le = (double)log10f(me + 1e-12f), lt = (double)log10f(mt + 1e-12f);
+#else
+          const double le = (double)__log10f(me + 1e-12f), lt = (double)__log10f(mt + 1e-12f);
+#endif
+          l_et = fma(le, lt, l_et);
+          l_tt = fma(lt, lt, l_tt);
+          l_ee = fma(le, le, l_ee);
+        }
+      };
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const cd za = special ? a[(8 - q) & 7] : b[7 - q];
+        const cd zb = special ? b[7 - q] : a[7 - q];
+        emit(ka + 256 * q, a[q], za);
+        emit(kb + 256 * q, b[q], zb);
+      }
+      if (special) emit(1024, a[4], a[4]);
+      if (want_lsd) {
+        const float w = warp_sum(lsd_acc);
+        if (lane == 0) lsd_part[fi][warp] = w;
+      }
+      pend_t = st;  // copied out after the next barrier (next frame's pass 1, or the item epilogue)
+      pend_e = se;
+    }
+    __syncthreads();
+    if (pend_t) {
+      for (int k = tid; k < F; k += kV2Threads) {
+        pend_t[k] = row_t[k + (k >> 4)];
+        if (pend_e) pend_e[k] = row_e[k + (k >> 4)];
+      }
+      pend_t = nullptr;
+    }
+    // ---- per-item reduction -> partials[item][0..7]
+    double lsd_sum = 0.0;
+    if (want_lsd && tid < nf) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sacc += lsd_part[tid][w];
+      lsd_sum = (double)sqrtf(sacc / (float)F);  // torch.mean(dim=3) ** 0.5 in float32
+    }
+    double vals[7] = {lsd_sum, s_et, s_tt, s_ee, l_et, l_tt, l_ee};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const double r = warp_sum(vals[i]);
+      if (lane == 0) red[warp][i] = r;
+    }
+    __syncthreads();
+    if (tid < 7) {
+      double r = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) r += red[w][tid];
+      partials[(size_t)item * kPartials + tid] = r;
+    }
+    __syncthreads();
+  }
+}
+
+
+}  // namespace ssr

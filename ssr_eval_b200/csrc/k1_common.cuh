@@ -1,0 +1,131 @@
+// k1_common.cuh -- device helpers, constants and plan-side structs shared by the K1 / K2 kernels.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/ssr_b200.h"
+#include "fft_core.cuh"
+
+namespace ssr {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxChunk = 64;   // frames per work item (upper bound)
+constexpr int kPartials = 8;    // doubles per work item
+constexpr int kSsimTR = 64;     // SSIM tile: output rows
+constexpr int kSsimTC = 256;    // SSIM tile: output cols (2 per thread)
+
+struct StftDev {
+  int n_fft, hop, F, M;
+  const cd* tw;            // exp(-2 pi i n / M)
+  const double* win_half;  // direct: 0.5 * window[n]
+  const uint16_t* ppos;    // direct: padded smem slot of frequency k after the DIF passes
+  const cd* cw;            // bluestein: 0.5 * window[n] * chirp[n]
+  const cd* bfilt;         // bluestein: FFT_M(conj chirp) / M in DIF (digit-reversed) order
+  const cd* cpost;         // bluestein: chirp[k]
+};
+
+// tables of the PFA path (n_fft = R * P, P <= 1024; see stft_tables.hpp)
+struct PfaDev {
+  int n_fft, hop, F, R, P;
+  const cd* tw;     // exp(-2 pi i n / 2048)
+  const cd* cwin;   // [r*P + n] = 0.5 * window[R n + r] * chirp_P[n]
+  const cd* post;   // [r*P + k] = chirp_P[k] * W_N^{rk}
+  const cd* bfilt;  // Bluestein filter spectrum / 2048, DIF (16,16,8) order
+  const cd* wr;     // [r*R + m] = W_R^{rm}
+};
+
+
+__host__ __device__ inline long long stft_frames(long long L, int n_fft, int hop) {
+  return 1 + (L + 2 * (n_fft / 2) - n_fft) / hop;
+}
+
+__device__ __forceinline__ long long reflect_index(long long i, long long L) {
+  if (i >= 0 && i < L) return i;
+  if (L == 1) return 0;
+  long long period = 2 * (L - 1);
+  i %= period;
+  if (i < 0) i += period;
+  return i < L ? i : period - i;
+}
+
+__device__ __forceinline__ float __fsqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+
+struct SyncThreads {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// setup: work-item table.  item_start[p] = first work item of pair p (item = chunk of <= `chunk`
+// consecutive frames), item_pair[item] = p, spec_off[p] = first spectrogram element of pair p.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_setup(const long long* __restrict__ offsets, int n, int n_fft, int hop, int chunk,
+                        int F, int* __restrict__ item_start, int* __restrict__ item_pair,
+                        long long* __restrict__ spec_off) {
+  __shared__ long long s_items[1024], s_frames[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, t * per), hi = min(n, lo + per);
+  long long it = 0, fr = 0;
+  for (int p = lo; p < hi; ++p) {
+    long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
+    it += (T + chunk - 1) / chunk;
+    fr += T;
+  }
+  s_items[t] = it;
+  s_frames[t] = fr;
+  __syncthreads();
+  if (t == 0) {
+    long long a = 0, b = 0;
+    for (int i = 0; i < 1024; ++i) {
+      long long x = s_items[i], y = s_frames[i];
+      s_items[i] = a;
+      s_frames[i] = b;
+      a += x;
+      b += y;
+    }
+  }
+  __syncthreads();
+  it = s_items[t];
+  fr = s_frames[t];
+  for (int p = lo; p < hi; ++p) {
+    long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
+    int nc = (int)((T + chunk - 1) / chunk);
+    item_start[p] = (int)it;
+    spec_off[p] = fr * F;
+    for (int c = 0; c < nc; ++c) item_pair[it + c] = p;
+    it += nc;
+    fr += T;
+  }
+  if (hi == n) {
+    item_start[n] = (int)it;
+    spec_off[n] = fr * F;
+  }
+}
+
+
+}  // namespace ssr

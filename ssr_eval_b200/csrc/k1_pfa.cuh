@@ -1,0 +1,269 @@
+// k1_pfa.cuh -- K1, PFA kernel for n_fft = R * P (R Bluestein sub-transforms on the 2048-point machinery).
+#pragma once
+#include "k1_common.cuh"
+#include "k1_map.cuh"
+
+namespace ssr {
+
+// ---------------------------------------------------------------------------------------------
+// K1 for non-power-of-two n_fft = R * P (2229 = 3 x 743 at 48 kHz -- the reference's own default --,
+// 1114, 743, 1486 ...): R Bluestein sub-transforms of length P on the 2048-point radix 16x16x8
+// machinery of k_stft_metrics_2048 (forward DIF, filter multiply and inverse butterfly of the last /
+// first pass in registers, inverse DIT), recombined with a radix-R butterfly on the fly in the
+// epilogue.  ~6 FFT-2048 per frame instead of 2 FFT-8192 (1.6x fewer flops, 2x less shared traffic
+// than the generic Bluestein kernel).  NQ = ceil(P / 128): pass-1 inputs / pass-3' outputs beyond
+// NQ are structurally zero / unused and are pruned at compile time.
+// ---------------------------------------------------------------------------------------------
+// 2 CTAs/SM (255 registers): the Bluestein filter values of the thread's two butterflies live in
+// registers and the samples + window*chirp factors of the NEXT sub-transform are fetched into registers
+// one sub-transform ahead -- the tables (103 KB) do not fit the L1 left beside the CTAs' shared memory,
+// so every table load is an L2 round trip that has to be hidden in software (measured: 21.6k -> 25.7k
+// pairs/s against the 3-CTA version that loaded in place).
+template <int NQ, int FIXED>
+__global__ void __launch_bounds__(kV2Threads, 2)
+k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restrict__ tgt,
+                   const long long* __restrict__ offsets, const int* __restrict__ item_start,
+                   const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
+                   double* __restrict__ partials, float* __restrict__ spec_e,
+                   float* __restrict__ spec_t, const long long* __restrict__ spec_off) {
+  constexpr int M = 2048, NW = kV2Threads / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* const buf = reinterpret_cast<cd*>(smem_raw);                       // M + M/8 slots
+  // Y_r, r < R-1, live behind buf; the LAST sub-transform's Y is written over buf itself (dead by then),
+  // which keeps the CTA at ~65 KB of shared memory = 3 CTAs per SM
+  cd* const Yx = reinterpret_cast<cd*>(smem_raw + sizeof(cd) * (M + M / 8));
+  __shared__ __align__(16) cd tw2[15 * 8];
+  __shared__ __align__(16) cd wr_s[16];
+  __shared__ float lsd_part[kMaxChunk][NW];
+  __shared__ double red[NW][kPartials];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = D.n_fft, F = D.F, hop = D.hop, R = D.R, P = D.P;
+  if (FIXED >= 0) flags = (unsigned)FIXED;
+  const bool want_lsd = flags & SSR_METRIC_LSD, want_log = flags & SSR_METRIC_LOG_SISPEC,
+             want_lin = flags & SSR_METRIC_SISPEC;
+  if (FIXED >= 0) {
+    spec_e = nullptr;
+    spec_t = nullptr;
+  }
+
+  cd tw1[15];
+#pragma unroll
+  for (int q = 1; q < 16; ++q) tw1[q - 1] = D.tw[tid * q];
+  if (tid < 120) tw2[tid] = D.tw[16 * (tid & 7) * ((tid >> 3) + 1)];
+  if (tid < R * R) wr_s[tid] = D.wr[tid];
+  int ia, ib;
+  v2_thread_butterflies(tid, &ia, &ib);
+  const int j2 = tid & 7;
+  cd* const b1 = buf + pad_idx(tid);
+  cd* const b2 = buf + pad_idx((tid >> 3) * 128 + j2);
+  cd* const b3a = buf + 9 * ia;
+  cd* const b3b = buf + 9 * ib;
+  const cd* const t2 = tw2 + j2;
+  __syncthreads();
+
+  cd fa[8], fb[8];  // Bluestein filter at this thread's 16 slots
+  {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      fa[q] = D.bfilt[8 * ia + q];
+      fb[q] = D.bfilt[8 * ib + q];
+    }
+  }
+
+  auto combine = [&](int kap) {  // Z[kap] = sum_r W_R^{r m} Y_r[k], kap = k + P m
+    int m = 0;
+    while (kap >= P) {
+      kap -= P;
+      ++m;
+    }
+    cd z = (R > 1) ? Yx[kap] : buf[kap];
+    if (R > 1) {
+      z = cmul(z, wr_s[m]);
+      for (int r = 1; r < R; ++r) {
+        const cd yv = (r == R - 1) ? buf[kap] : Yx[r * P + kap];
+        z = cadd(z, cmul(yv, wr_s[r * R + m]));
+      }
+    }
+    return z;
+  };
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int p = item_pair[item];
+    const int c = item - item_start[p];
+    const long long off = offsets[p];
+    const long long L = offsets[p + 1] - off;
+    const long long T = stft_frames(L, N, hop);
+    const long long f0 = (long long)c * chunk;
+    const int nf = (int)min((long long)chunk, T - f0);
+    const float* xe = est + off;
+    const float* xt = tgt + off;
+    double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
+
+    // inputs of sub-transform (f, r): samples of both signals and window*chirp, NQ per thread
+    float ptx[NQ], pex[NQ];
+    cd pcw[NQ];
+    auto fetch_inputs = [&](long long f, int r) {
+      const long long start = f * hop - N / 2;
+      const bool interior = (start >= 0 && start + N <= L);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int n = tid + 128 * q;
+        ptx[q] = 0.f;
+        pex[q] = 0.f;
+        pcw[q] = cd{0.0, 0.0};
+        if (n < P) {
+          const long long si = start + (long long)R * n + r;
+          const long long idx = interior ? si : reflect_index(si, L);
+          ptx[q] = __ldg(xt + idx);
+          pex[q] = __ldg(xe + idx);
+          pcw[q] = D.cwin[r * P + n];
+        }
+      }
+    };
+    fetch_inputs(f0, 0);
+
+    for (int fi = 0; fi < nf; ++fi) {
+      const long long f = f0 + fi;
+      for (int r = 0; r < R; ++r) {
+        cd v[16];
+        // ---- forward pass 1: a[n] = z[R n + r] * (0.5 window * chirp), zero padded to 2048
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          v[q] = cd{0.0, 0.0};
+          if (q < NQ) {
+            const double tt = (double)ptx[q], ee = (double)pex[q];
+            v[q] = cd{tt * pcw[q].x - ee * pcw[q].y, tt * pcw[q].y + ee * pcw[q].x};
+          }
+        }
+        // the loads of the next sub-transform fly during all passes of this one
+        if (r + 1 < R) fetch_inputs(f, r + 1);
+        else if (fi + 1 < nf) fetch_inputs(f + 1, 0);
+        bfly16<false>(v);
+#pragma unroll
+        for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw1[q - 1]);
+        __syncthreads();  // previous sub-transform's last loads are done
+#pragma unroll
+        for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
+        __syncthreads();
+        // ---- forward pass 2
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = b2[9 * q];
+        bfly16<false>(v);
+        b2[0] = v[0];
+#pragma unroll
+        for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
+        __syncthreads();
+        // ---- forward pass 3, Bluestein filter, inverse pass 1: all in registers
+        cd* a = v;
+        cd* b = v + 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          a[q] = b3a[q];
+          b[q] = b3b[q];
+        }
+        bfly8<false>(a);
+        bfly8<false>(b);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          a[q] = cmul(a[q], fa[q]);
+          b[q] = cmul(b[q], fb[q]);
+        }
+        bfly8<true>(a);
+        bfly8<true>(b);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          b3a[q] = a[q];
+          b3b[q] = b[q];
+        }
+        __syncthreads();
+        // ---- inverse pass 2
+        v[0] = b2[0];
+#pragma unroll
+        for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b2[9 * q], t2[(q - 1) * 8]);
+        bfly16<true>(v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) b2[9 * q] = v[q];
+        __syncthreads();
+        // ---- inverse pass 3 -> conv[k], k = tid + 128 q; Y_r[k] = conv[k] * chirp[k] * W_N^{rk}
+        v[0] = b1[0];
+#pragma unroll
+        for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b1[144 * q], tw1[q - 1]);
+        bfly16<true>(v);
+        cd* Yr = Yx + r * P;
+        if (r == R - 1) {
+          __syncthreads();  // every thread has finished reading buf
+          Yr = buf;
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int k = tid + 128 * q;
+          if (k < P) Yr[k] = cmul(v[q], D.post[r * P + k]);
+        }
+      }
+      __syncthreads();
+      // ---- epilogue over the F bins (recombination on the fly)
+      float lsd_acc = 0.f;
+      float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
+      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
+      for (int k = tid; k < F; k += kV2Threads) {
+        const cd zk = combine(k);
+        const cd zn = combine(k ? N - k : 0);
+        const float tre = (float)(zk.x + zn.x), tim = (float)(zk.y - zn.y);
+        const float ere = (float)(zk.y + zn.y), eim = (float)(zn.x - zk.x);
+        const float tx = tre * tre + tim * tim;
+        const float ey = ere * ere + eim * eim;
+        const float me = __fsqrt_approx(ey);
+        const float mt = (st || want_lin || want_log) ? __fsqrt_approx(tx) : 0.f;
+        if (st) st[k] = mt;
+        if (se) se[k] = me;
+        if (want_lsd) {
+          const float den = me + 1e-12f;
+          const float l = __log10f(__fdividef(tx, den * den) + 1e-12f);
+          lsd_acc += l * l;
+        }
+        if (want_lin) {
+          const double de = (double)me, dt = (double)mt;
+          s_et = fma(de, dt, s_et);
+          s_tt = fma(dt, dt, s_tt);
+          s_ee = fma(de, de, s_ee);
+        }
+        if (want_log) {
+          const double le = (double)__log10f(me + 1e-12f), lt = (double)__log10f(mt + 1e-12f);
+          l_et = fma(le, lt, l_et);
+          l_tt = fma(lt, lt, l_tt);
+          l_ee = fma(le, le, l_ee);
+        }
+      }
+      if (want_lsd) {
+        const float w = warp_sum(lsd_acc);
+        if (lane == 0) lsd_part[fi][warp] = w;
+      }
+    }
+    __syncthreads();
+    double lsd_sum = 0.0;
+    if (want_lsd && tid < nf) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sacc += lsd_part[tid][w];
+      lsd_sum = (double)sqrtf(sacc / (float)F);
+    }
+    double vals[7] = {lsd_sum, s_et, s_tt, s_ee, l_et, l_tt, l_ee};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const double rr = warp_sum(vals[i]);
+      if (lane == 0) red[warp][i] = rr;
+    }
+    __syncthreads();
+    if (tid < 7) {
+      double rr = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) rr += red[w][tid];
+      partials[(size_t)item * kPartials + tid] = rr;
+    }
+    __syncthreads();
+  }
+}
+
+
+}  // namespace ssr

@@ -1,0 +1,195 @@
+// k2_ssim.cuh -- K2 (7x7 box-window SSIM, cp.async row pipeline) and the fixed-order finalize kernel.
+#pragma once
+#include "k1_common.cuh"
+
+namespace ssr {
+
+// ---------------------------------------------------------------------------------------------
+// K2: SSIM of two (T, F) float32 magnitude images, valid 7x7 windows only (skimage crops the
+// 3-pixel border, so the reflect boundary mode of uniform_filter never reaches the mean).
+// One CTA = one tile of kSsimTR x kSsimTC window positions, 128 threads, TWO adjacent columns per
+// thread.  Rows stream through a double-buffered shared row buffer; per row a thread forms the
+// horizontal 7-sums of (x, y, xx, yy, xy) for its two columns (sliding: the second column reuses the
+// first column's inner sum) and updates RUNNING vertical 7-sums: V += h_new - h_oldest, with the last
+// seven h kept in a register ring (unrolled-by-7 loop).  The running sums restart in every tile, so
+// the result does not depend on how the batch was partitioned.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSsimThreads = 128;
+
+__global__ void __launch_bounds__(kSsimThreads)
+k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
+       const long long* __restrict__ spec_off, const long long* __restrict__ offsets, int pair0,
+       int n_fft, int hop, int F, int tiles_x, int tiles_per_pair, double* __restrict__ ssim_part) {
+  const int p = pair0 + blockIdx.y;
+  const int tile = blockIdx.x;
+  const int ty = tile / tiles_x, tx = tile % tiles_x;
+  const long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
+  const int rows_out = (int)T - 6, cols_out = F - 6;
+  const int r0 = ty * kSsimTR;
+  double* out = ssim_part + (size_t)p * tiles_per_pair + tile;
+  if (r0 >= rows_out || cols_out <= 0) {
+    if (threadIdx.x == 0) *out = 0.0;
+    return;
+  }
+  const int r_end = min(r0 + kSsimTR, rows_out) + 6;  // input rows [r0, r_end)
+  const int c0 = tx * kSsimTC;
+  const int t = threadIdx.x;
+  const int c = 2 * t;  // first of this thread's two columns inside the tile
+  const bool ok0 = (c0 + c) < cols_out, ok1 = (c0 + c + 1) < cols_out;
+  const float* E = spec_e + spec_off[p];
+  const float* G = spec_t + spec_off[p];
+  constexpr int RB = kSsimTC + 8, STAGES = 4;
+  __shared__ __align__(16) float rowbuf[STAGES][2][RB];
+  __shared__ double red[kSsimThreads / 32];
+
+  float ring[7][10];
+#pragma unroll
+  for (int s = 0; s < 7; ++s)
+#pragma unroll
+    for (int q = 0; q < 10; ++q) ring[s][q] = 0.f;
+  float V[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) V[q] = 0.f;
+  float acc = 0.f;
+  const float inv49 = 1.0f / 49.0f, cov_norm = 49.0f / 48.0f;
+  const float C1 = 0.0004f, C2 = 0.0036f;  // (0.01*2)^2, (0.03*2)^2
+
+  // rows stream global -> shared with cp.async (LDGSTS), STAGES-1 rows in flight; columns beyond the
+  // image are zero-filled by the copy itself (src-size 0)
+  auto issue_row = [&](int r) {
+    if (r < r_end) {
+      const int stg = (r - r0) % STAGES;
+      const float* er = E + (long long)r * F + c0;
+      const float* gr = G + (long long)r * F + c0;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int col = t + u * kSsimThreads;
+        if (u < 2 || t < 8) {
+          const bool in = (c0 + col) < F;
+          cp_async4(&rowbuf[stg][0][col], in ? er + col : er, in ? 4 : 0);
+          cp_async4(&rowbuf[stg][1][col], in ? gr + col : gr, in ? 4 : 0);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int k = 0; k < STAGES - 1; ++k) issue_row(r0 + k);
+
+  for (int rb = r0; rb < r_end; rb += 7) {
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+      const int r = rb + s;
+      if (r < r_end) {  // uniform across the CTA
+        const int par = (r - r0) % STAGES;
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+        __syncthreads();               // row r has landed for everyone; row r-1 is fully consumed
+        issue_row(r + STAGES - 1);     // refills the stage row r-1 occupied
+        float x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 xv = *reinterpret_cast<const float2*>(&rowbuf[par][0][c + 2 * j]);
+          const float2 yv = *reinterpret_cast<const float2*>(&rowbuf[par][1][c + 2 * j]);
+          x[2 * j] = xv.x;
+          x[2 * j + 1] = xv.y;
+          y[2 * j] = yv.x;
+          y[2 * j + 1] = yv.y;
+        }
+        // inner sums over columns c+1 .. c+6, then the two outputs add their own end column
+        float ix = 0.f, iy = 0.f, ixx = 0.f, iyy = 0.f, ixy = 0.f;
+#pragma unroll
+        for (int j = 1; j < 7; ++j) {
+          ix += x[j];
+          iy += y[j];
+          ixx += x[j] * x[j];
+          iyy += y[j] * y[j];
+          ixy += x[j] * y[j];
+        }
+        float h[10];
+        h[0] = ix + x[0];
+        h[1] = iy + y[0];
+        h[2] = ixx + x[0] * x[0];
+        h[3] = iyy + y[0] * y[0];
+        h[4] = ixy + x[0] * y[0];
+        h[5] = ix + x[7];
+        h[6] = iy + y[7];
+        h[7] = ixx + x[7] * x[7];
+        h[8] = iyy + y[7] * y[7];
+        h[9] = ixy + x[7] * y[7];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          V[q] += h[q] - ring[s][q];
+          ring[s][q] = h[q];
+        }
+        if (r - r0 >= 6) {
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const float ux = V[5 * o] * inv49, uy = V[5 * o + 1] * inv49;
+            const float uxx = V[5 * o + 2] * inv49, uyy = V[5 * o + 3] * inv49, uxy = V[5 * o + 4] * inv49;
+            const float vx = cov_norm * (uxx - ux * ux);
+            const float vy = cov_norm * (uyy - uy * uy);
+            const float vxy = cov_norm * (uxy - ux * uy);
+            const float A1 = 2.f * ux * uy + C1, A2 = 2.f * vxy + C2;
+            const float B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+            const float S = __fdividef(A1 * A2, B1 * B2);
+            if (o == 0 ? ok0 : ok1) acc += S;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  double r = warp_sum((double)acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = r;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    for (int w = 0; w < kSsimThreads / 32; ++w) sum += red[w];
+    *out = sum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: fixed-order sum of the per-item partials -> the four metrics of each pair (float64).
+// ---------------------------------------------------------------------------------------------
+__device__ inline double sispec_from_sums(double s_et, double s_tt, double s_ee) {
+  const double EPS = 1e-12;
+  double alpha = s_et / (s_tt + EPS);            // energy_unify: target' = alpha * target
+  double tt = alpha * alpha * s_tt;              // ||target'||^2
+  double nn = s_ee - 2.0 * alpha * s_et + tt;    // ||est - target'||^2
+  if (nn < 0.0) nn = 0.0;
+  return 10.0 * log10(tt / (nn + EPS) + EPS);
+}
+
+__global__ void __launch_bounds__(128)
+k_finalize(const long long* __restrict__ offsets, int n, int n_fft, int hop, int F,
+           const int* __restrict__ item_start, const double* __restrict__ partials,
+           const double* __restrict__ ssim_part, int tiles_per_pair, unsigned flags,
+           double* __restrict__ out) {
+  // one warp per pair; lanes stride over the items / tiles, then a fixed-shape shuffle tree:
+  // the summation order depends only on the pair's own item / tile count
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= n) return;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  const long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int it = item_start[p] + lane; it < item_start[p + 1]; it += 32)
+#pragma unroll
+    for (int i = 0; i < 7; ++i) v[i] += partials[(size_t)it * kPartials + i];
+  double s = 0.0;
+  if (flags & SSR_METRIC_SSIM)
+    for (int t = lane; t < tiles_per_pair; t += 32) s += ssim_part[(size_t)p * tiles_per_pair + t];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) v[i] = warp_sum(v[i]);
+  s = warp_sum(s);
+  if (lane != 0) return;
+  out[p * 4 + 0] = (flags & SSR_METRIC_LSD) ? v[0] / (double)T : nan;
+  out[p * 4 + 1] = (flags & SSR_METRIC_LOG_SISPEC) ? sispec_from_sums(v[4], v[5], v[6]) : nan;
+  out[p * 4 + 2] = (flags & SSR_METRIC_SISPEC) ? sispec_from_sums(v[1], v[2], v[3]) : nan;
+  const double cnt = (double)(T - 6) * (double)(F - 6);
+  out[p * 4 + 3] = ((flags & SSR_METRIC_SSIM) && T > 6 && F > 6) ? s / cnt : nan;
+}
+
+
+}  // namespace ssr

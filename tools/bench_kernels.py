@@ -53,7 +53,7 @@ def main():
         eng = StftMetrics(2048, 512)
         out = torch.empty((n, 4), dtype=torch.float64, device=dev)
         for flags, name in ((1, "K1 2048/512 LSD"), (7, "K1 2048/512 LSD+log_sispec+sispec"),
-                            (15, "K1+K2 2048/512 all four (L2-sized sub-batches)")):
+                            (15, "K1+K2 2048/512 all four")):
             ms = timeit(lambda: eng.metrics_device(est, tgt, off, flags, offsets_dev=off_d, out=out))
             report(name, ms, n, "pairs", n * (8 * L + 32))
         del tgt, est
