@@ -359,3 +359,21 @@ def test_helper_subsampling_and_iir_settings(tmp_path, monkeypatch):
     for k in d:
         want = oracle.evaluation(d[k].astype(np.float32), x, rate=44100)
         _assert_metrics(res["p1"]["a.wav"][k], want, k)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(1024, 256), (4096, 1024), (512, 100), (1031, 300), (100, 25), (2048, 441),
+                                         (2048, 3000), (1486, 320)])
+def test_unusual_stft_sizes_vs_oracle(engines, n_fft, hop):
+    """Every K1 code path: generic direct (1024 / 4096 / 512), generic Bluestein (prime 1031 > 1024),
+    PFA with R = 1 (100) and R = 2 (1486), the 2048 kernel at the reference's 44.1 kHz hop (441) and at a
+    hop larger than the frame."""
+    lengths = [3 * n_fft + 17, 9 * n_fft + 1, 20000]
+    tgt = [speech_like(n, sr=48000, seed=400 + i) for i, n in enumerate(lengths)]
+    est = [(t * 0.7 + 3e-3 * np.random.default_rng(i).standard_normal(len(t))).astype(np.float32)
+           for i, t in enumerate(tgt)]
+    got = engines(n_fft, hop).metrics(est, tgt)
+    for i in range(len(lengths)):
+        frames = 1 + (lengths[i] + 2 * (n_fft // 2) - n_fft) // hop
+        which = METRICS if frames >= 7 else METRICS[:3]
+        want = oracle.evaluation(est[i], tgt[i], n_fft=n_fft, hop=hop, which=which)
+        _assert_metrics(dict(zip(METRICS, got[i])), want, f"n_fft {n_fft} hop {hop} L {lengths[i]}")

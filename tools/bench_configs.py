@@ -86,11 +86,16 @@ def cfg5(dev, speakers=8, utts=300):
     speaker_of = np.repeat(np.arange(speakers), utts)
     ids = dist.shard_indices(len(lengths), rank, world)
     mine = lengths[ids]
+    # the SAME synthetic set on every rank / world size (fixed seed), then this rank's shard of it, so the
+    # aggregated result must not depend on the number of GPUs
     g = torch.Generator(device=dev)
-    g.manual_seed(50 + rank)
-    total = int(mine.sum())
-    tgt = 0.1 * torch.randn(total, generator=g, device=dev)
-    est = tgt + 1e-3 * torch.randn(total, generator=g, device=dev)
+    g.manual_seed(50)
+    all_off = offsets_of(lengths)
+    full_t = 0.1 * torch.randn(int(all_off[-1]), generator=g, device=dev)
+    full_e = full_t + 1e-3 * torch.randn(int(all_off[-1]), generator=g, device=dev)
+    tgt = torch.cat([full_t[all_off[i]:all_off[i + 1]] for i in ids])
+    est = torch.cat([full_e[all_off[i]:all_off[i + 1]] for i in ids])
+    del full_t, full_e
     off = offsets_of(mine)
     off_d = torch.from_numpy(off).to(dev)
     eng = StftMetrics(2229, 480)  # AudioMetrics(48000): metrics.py:18-19
@@ -117,7 +122,7 @@ def cfg5(dev, speakers=8, utts=300):
         print(json.dumps({"config": "cfg5", "world": world, "pairs": int(len(lengths)), "n_fft": 2229, "hop": 480,
                           "wall_ms_incl_d2h_and_allreduce": round(dt * 1e3, 2),
                           "pairs_per_s": round(len(lengths) / dt, 1),
-                          "averaged": [round(float(v), 5) for v in avg]}), flush=True)
+                          "averaged": [round(float(v), 10) for v in avg]}), flush=True)
 
 
 def main():
