@@ -136,6 +136,19 @@ int ssr_stft_splice_istft_batched(const ssr_splice_plan* plan, const float* x_de
                                   const int64_t* offsets_host, const int64_t* offsets_dev, int n,
                                   const int32_t* cut_bins_dev, float* y_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K7 ("next" row): zero-phase IIR filtering = scipy.signal.sosfiltfilt(sos, x)
+ * with the default odd padding, the recursion behind lowpass_filter / bandpass_filter
+ * (ssr_eval/lowpass.py:54-131).  The filter design stays on the host (scipy, as in the reference):
+ * sos_host = n_sections x 6 float64 (a0 == 1), zi_host = scipy.signal.sosfilt_zi(sos) (n_sections x 2),
+ * edge = scipy's default padlen = 3 * ntaps.  Input float32, output float64 (scipy's result type).
+ * Every utterance must be longer than `edge`.  Workspace: ssr_sosfiltfilt_workspace_bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t ssr_sosfiltfilt_workspace_bytes(const int64_t* offsets_host, int n, int edge);
+int ssr_sosfiltfilt_batched(const double* sos_host, int n_sections, const double* zi_host, int edge,
+                            const float* x_dev, const int64_t* offsets_host, const int64_t* offsets_dev,
+                            int n, double* y_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

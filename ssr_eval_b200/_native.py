@@ -56,6 +56,9 @@ def lib():
     L.ssr_splice_plan_create.argtypes = [ctypes.POINTER(vp), c_int, c_int]
     L.ssr_splice_plan_destroy.argtypes = [vp]
     L.ssr_stft_splice_istft_batched.argtypes = [vp, vp, vp, vp, vp, c_int, vp, vp, vp]
+    L.ssr_sosfiltfilt_workspace_bytes.argtypes = [vp, c_int, c_int]
+    L.ssr_sosfiltfilt_workspace_bytes.restype = c_sz
+    L.ssr_sosfiltfilt_batched.argtypes = [vp, c_int, vp, c_int, vp, vp, vp, c_int, vp, vp, c_sz, vp]
     _lib = L
     return L
 
@@ -89,4 +92,5 @@ EXPORTED_SYMBOLS = (
     "ssr_resample_poly_batched",
     "ssr_lowpass_plan_create", "ssr_lowpass_plan_destroy", "ssr_stft_hard_lowpass_batched",
     "ssr_splice_plan_create", "ssr_splice_plan_destroy", "ssr_stft_splice_istft_batched",
+    "ssr_sosfiltfilt_workspace_bytes", "ssr_sosfiltfilt_batched",
 )

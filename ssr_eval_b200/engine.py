@@ -308,6 +308,34 @@ class SpliceIstft:
         return [yh[s:e].copy() for s, e in zip(off[:-1], off[1:])]
 
 
+def sosfiltfilt_batch(sos, wav_list):
+    """K7: scipy.signal.sosfiltfilt(sos, x) (default odd padding) for a batch of float32 utterances ->
+    list of float64 arrays.  Filter design, sosfilt_zi and the pad length are scipy's, on the host."""
+    from scipy.signal import sosfilt_zi
+    _require_cuda()
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    assert sos.ndim == 2 and sos.shape[1] == 6
+    n_sections = sos.shape[0]
+    ntaps = 2 * n_sections + 1
+    ntaps -= min(int((sos[:, 2] == 0).sum()), int((sos[:, 5] == 0).sum()))
+    edge = 3 * ntaps  # scipy's default padlen
+    for w in wav_list:
+        if len(w) <= edge:
+            raise ValueError("The length of the input vector x must be greater than padlen, which is %d." % edge)
+    zi = np.ascontiguousarray(sosfilt_zi(sos), dtype=np.float64)
+    x_h, off = pack_ragged(wav_list, pinned=True)
+    x_d = x_h.cuda(non_blocking=True)
+    off_d = torch.from_numpy(off).to(x_d.device)
+    y = torch.empty(int(off[-1]), dtype=torch.float64, device=x_d.device)
+    need = N.lib().ssr_sosfiltfilt_workspace_bytes(_np_ptr(off), len(wav_list), edge)
+    ws = torch.empty(max(int(need), 8), dtype=torch.uint8, device=x_d.device)
+    N.check(N.lib().ssr_sosfiltfilt_batched(_np_ptr(sos), n_sections, _np_ptr(zi), edge, _ptr(x_d), _np_ptr(off),
+                                            _ptr(off_d), len(wav_list), _ptr(y), _ptr(ws), ws.numel(), _stream()),
+            "ssr_sosfiltfilt_batched")
+    yh = y.cpu().numpy()
+    return [yh[s:e].copy() for s, e in zip(off[:-1], off[1:])]
+
+
 class HostPipeline:
     """Host-buffer entry point of K1/K2: (pinned) host batches are streamed to the GPU in chunks on a
     copy stream, double-buffered against the kernels, and the (n, 4) float64 result is read back.

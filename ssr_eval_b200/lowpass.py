@@ -1,12 +1,12 @@
 """Low-resolution simulation with the reference's interface (ssr_eval/lowpass.py).
 
-``stft_hard`` (K4) and ``subsampling`` (K3 twice) run on the GPU kernels; the IIR zero-phase filters
-(butter / cheby1 / ellip / bessel via sosfiltfilt) are out of the hot-path scope (SURVEY.md section 2
-row 3, section 8f row 3) and stay a scipy passthrough so the API is complete."""
+``stft_hard`` (K4), ``subsampling`` (K3 twice) and the IIR zero-phase filters (butter / cheby1 / ellip /
+bessel: scipy designs the second-order sections on the host exactly as the reference does, the
+``sosfiltfilt`` recursion runs in kernel K7) all execute on the GPU; there is no CPU fallback."""
 import numpy as np
-from scipy.signal import butter, cheby1, cheby2, ellip, bessel, sosfiltfilt
+from scipy.signal import butter, cheby1, cheby2, ellip, bessel
 
-from .engine import HardLowpass, PolyphaseResampler
+from .engine import HardLowpass, PolyphaseResampler, sosfiltfilt_batch
 
 _hard = {}
 _resamplers = {}
@@ -73,15 +73,20 @@ def _design(order, band, btype, ftype):
     raise Exception(f"The {btype}pass filter {ftype} is not supported!")
 
 
+def sosfiltfilt(sos, x):
+    """scipy.signal.sosfiltfilt(sos, x) for one 1-D signal, on the GPU (K7); float64 result."""
+    return sosfiltfilt_batch(sos, [np.asarray(x, dtype=np.float32)])[0]
+
+
 def lowpass_filter(x, highcut, fs, order, ftype):
-    """Zero-phase IIR low-pass (ssr_eval/lowpass.py:94-131) -- scipy passthrough."""
+    """Zero-phase IIR low-pass (ssr_eval/lowpass.py:94-131): scipy design + GPU sosfiltfilt."""
     sos = _design(order, highcut / (0.5 * fs), "low", ftype)
     y = sosfiltfilt(sos, x)
     return align_length(x, y) if len(y) != len(x) else y
 
 
 def bandpass_filter(x, lowcut, highcut, fs, order, ftype):
-    """Zero-phase IIR band-pass (ssr_eval/lowpass.py:54-91) -- scipy passthrough."""
+    """Zero-phase IIR band-pass (ssr_eval/lowpass.py:54-91): scipy design + GPU sosfiltfilt."""
     nyq = 0.5 * fs
     sos = _design(order, [lowcut / nyq, highcut / nyq], "band", ftype)
     y = sosfiltfilt(sos, x)

@@ -37,9 +37,6 @@ def test_lowpass_dispatch_errors_and_iir():
         lowpass(x[:, None], 1000, 44100, _type="stft_hard")
     with pytest.raises(ValueError):
         lowpass(x, 1000, 44100, _type="nope")
-    from scipy.signal import butter, sosfiltfilt
-    y = lowpass(x, 8000, 44100, order=12, _type="butter")  # order clamped to 10
-    np.testing.assert_allclose(y, sosfiltfilt(butter(10, 8000 / 22050, btype="low", output="sos"), x))
     assert limit(1, 10, 2) == 2 and limit(11, 10, 2) == 10 and limit(5.0, 10, 2) == 5
     assert len(align_length(np.zeros(10), np.zeros(7))) == 10
     assert len(align_length(np.zeros(10), np.zeros(17))) == 10

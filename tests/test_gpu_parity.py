@@ -220,10 +220,12 @@ def test_stft_hard_lowpass_goldens(golden):
     x = golden["LP/x"]
     for case in golden["lp_cases"]:
         kind, cutoff, fs = str(case).rsplit("_", 2)
-        if kind == "butter":
+        want = golden[f"LP/{case}"]
+        if kind == "butter":  # IIR path (K7): float64, golden produced by the reference's lowpass(order=8)
+            y = lowpass(x, int(cutoff), int(fs), order=8, _type=kind)
+            assert y.dtype == np.float64 and np.abs(y - want).max() <= 1e-12
             continue
         y = lowpass(x, int(cutoff), int(fs), order=1, _type=kind)
-        want = golden[f"LP/{case}"]
         assert y.shape == want.shape and y.dtype == np.float32
         tol = 2e-5 if kind == "stft_hard" else 1e-6
         assert np.abs(y - want).max() <= tol, (case, np.abs(y - want).max())
@@ -377,3 +379,36 @@ def test_unusual_stft_sizes_vs_oracle(engines, n_fft, hop):
         which = METRICS if frames >= 7 else METRICS[:3]
         want = oracle.evaluation(est[i], tgt[i], n_fft=n_fft, hop=hop, which=which)
         _assert_metrics(dict(zip(METRICS, got[i])), want, f"n_fft {n_fft} hop {hop} L {lengths[i]}")
+
+
+def test_sosfiltfilt_vs_scipy():
+    """K7 against the installed scipy (the same upstream code the reference calls): all four IIR families,
+    low-pass and band-pass, orders 2..10 (order clamp of lowpass()), ragged batch.  float64 recursion with
+    scipy's operation order: <= 1e-12 relative to the signal (normally bit-exact)."""
+    from scipy.signal import butter, cheby1, ellip, bessel, sosfiltfilt
+    from ssr_eval_b200 import lowpass
+    from ssr_eval_b200.lowpass import bandpass
+    from ssr_eval_b200.engine import sosfiltfilt_batch
+    x = speech_like(22050, sr=44100, seed=61)
+    designs = {"butter": lambda o, w: butter(o, w, btype="low", output="sos"),
+               "cheby1": lambda o, w: cheby1(o, 0.1, w, btype="low", output="sos"),
+               "ellip": lambda o, w: ellip(o, 0.1, 60, w, btype="low", output="sos"),
+               "bessel": lambda o, w: bessel(o, w, btype="low", output="sos")}
+    n_exact = 0
+    for name, mk in designs.items():
+        for order in (2, 5, 12):
+            y = lowpass(x, 6000, 44100, order=order, _type=name)
+            want = sosfiltfilt(mk(min(max(order, 2), 10), 6000 / 22050), x)
+            assert y.dtype == np.float64 and y.shape == want.shape
+            assert np.abs(y - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), (name, order, np.abs(y - want).max())
+            n_exact += int(np.array_equal(y, want))
+    yb = bandpass(x, 1000, 5000, 44100, order=4, _type="butter")
+    wb = sosfiltfilt(butter(4, [1000 / 22050, 5000 / 22050], btype="band", output="sos"), x)
+    assert np.abs(yb - wb).max() <= 1e-12
+    sos = butter(8, 0.3, output="sos")
+    waves = [speech_like(n, 16000, seed=70 + i) for i, n in enumerate((28, 100, 4001, 16000))]
+    for w, y in zip(waves, sosfiltfilt_batch(sos, waves)):
+        assert np.abs(y - sosfiltfilt(sos, w)).max() <= 1e-12
+    with pytest.raises(ValueError):
+        sosfiltfilt_batch(sos, [waves[0][:27]])
+    print(f"sosfiltfilt: {n_exact}/12 single-signal cases bit-exact vs scipy")
