@@ -55,36 +55,57 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   const float C1 = 0.0004f, C2 = 0.0036f;  // (0.01*2)^2, (0.03*2)^2
 
   // rows stream global -> shared with cp.async (LDGSTS), STAGES-1 rows in flight; columns beyond the
-  // image are zero-filled by the copy itself (src-size 0)
-  auto issue_row = [&](int r) {
-    if (r < r_end) {
-      const int stg = (r - r0) % STAGES;
-      const float* er = E + (long long)r * F + c0;
-      const float* gr = G + (long long)r * F + c0;
+  // image are zero-filled by the copy itself (src-size 0).  All per-row address arithmetic is kept in
+  // running pointers / counters (the copy engine work is 6 LDGSTS per thread and row).
+  int coff[3], cbytes[3];
+  unsigned sdst[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int col = t + u * kSsimThreads;
+    const bool use = (u < 2 || t < 8);
+    const bool in = use && (c0 + col) < F;
+    coff[u] = in ? col : 0;
+    cbytes[u] = in ? 4 : 0;
+    sdst[u] = (unsigned)__cvta_generic_to_shared(&rowbuf[0][0][use ? col : 0]);
+  }
+  const float* e_next = E + (long long)r0 * F + c0;  // row to be issued next
+  const float* g_next = G + (long long)r0 * F + c0;
+  int rows_left = r_end - r0;
+  int stage_next = 0;
+  constexpr unsigned kStageBytes = 2 * RB * sizeof(float), kImgBytes = RB * sizeof(float);
+  auto issue_row = [&]() {
+    if (rows_left > 0) {
+      const unsigned sb = stage_next * kStageBytes;
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
-        const int col = t + u * kSsimThreads;
         if (u < 2 || t < 8) {
-          const bool in = (c0 + col) < F;
-          cp_async4(&rowbuf[stg][0][col], in ? er + col : er, in ? 4 : 0);
-          cp_async4(&rowbuf[stg][1][col], in ? gr + col : gr, in ? 4 : 0);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst[u] + sb), "l"(e_next + coff[u]),
+                       "r"(cbytes[u])
+                       : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst[u] + sb + kImgBytes),
+                       "l"(g_next + coff[u]), "r"(cbytes[u])
+                       : "memory");
         }
       }
+      e_next += F;
+      g_next += F;
+      --rows_left;
+      stage_next = (stage_next + 1 == STAGES) ? 0 : stage_next + 1;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 #pragma unroll
-  for (int k = 0; k < STAGES - 1; ++k) issue_row(r0 + k);
+  for (int k = 0; k < STAGES - 1; ++k) issue_row();
+  int par = 0;  // stage holding the row being consumed
 
   for (int rb = r0; rb < r_end; rb += 7) {
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
       const int r = rb + s;
       if (r < r_end) {  // uniform across the CTA
-        const int par = (r - r0) % STAGES;
         asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
-        __syncthreads();               // row r has landed for everyone; row r-1 is fully consumed
-        issue_row(r + STAGES - 1);     // refills the stage row r-1 occupied
+        __syncthreads();  // row r has landed for everyone; row r-1 is fully consumed
+        issue_row();      // refills the stage row r-1 occupied
         float x[8], y[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -135,6 +156,7 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
             if (o == 0 ? ok0 : ok1) acc += S;
           }
         }
+        par = (par + 1 == STAGES) ? 0 : par + 1;
       }
     }
   }
