@@ -2,14 +2,22 @@
 #pragma once
 #include "k1_common.cuh"
 #include "k1_map.cuh"
+#include "tmem.cuh"
 
 namespace ssr {
 
 // ---------------------------------------------------------------------------------------------
 // K1, specialised: n_fft = 2048 (BASELINE config 2 and every evaluation at 44.1 kHz).
 // 128 threads, 16 points per thread: radix 16 x 16 x 8 in-place DIF.
-//   pass 1: samples come straight from global memory (coalesced, window folded in), the 15
-//           pass-1 twiddles of a thread never change and live in registers for the CTA's lifetime;
+//   pass 1: samples come from global memory (coalesced, window folded in); the 15 pass-1 twiddles
+//           of a thread never change and live in TENSOR MEMORY (60 columns of the thread's TMEM lane,
+//           written once with tcgen05.st, fetched per frame with tcgen05.ld in four double-buffered
+//           chunks): 60 registers less than keeping them in the register file, which is what lets
+//           4 CTAs (16 warps) share an SM, and no LSU / shared-memory bandwidth;
+//           RING (hop == 512 == 4 x 128): a thread's 16 (target, est) samples of a frame are the same
+//           as the previous frame's shifted by 4, so they are kept -- already converted to float64 --
+//           in a 64-column TMEM ring; an interior frame loads only its 4 new samples per signal from
+//           global memory (one frame ahead, into 8 registers) and converts 8 instead of 32 values;
 //   pass 2: twiddles W_128^{jq} (120 values) from a conflict-free shared table;
 //   pass 3: no twiddles; every thread transforms a butterfly AND its Hermitian partner
 //           (k1_map.cuh), so Z[k] and Z[N-k] meet in registers and the epilogue needs no
@@ -20,69 +28,16 @@ namespace ssr {
 // spectrograms are written for K2); hot configurations: 1 = LSD only, 7 = LSD + log-sispec + sispec,
 // 15 = those + spectrograms.  FIXED < 0: run-time flags.
 
-// ---- tensor-memory helpers (32x32b shape: thread i of warp w <-> TMEM lane 32 w + i, consecutive columns)
-#define SSR_R16(a) a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]
-__device__ __forceinline__ void tmem_ld16(unsigned addr, unsigned (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(addr)
-      : "memory");
-}
-// wait for the outstanding tcgen05.ld of this thread; the registers are operands so that no use of them
-// can be scheduled ahead of the wait
-__device__ __forceinline__ void tmem_wait_ld(unsigned (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tmem_pin(unsigned (&r)[16]) {  // orders uses of r after the preceding wait
-  asm volatile(""
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st16(unsigned addr, const unsigned (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void pack4(const cd* v, unsigned (&r)[16]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    r[4 * i + 0] = (unsigned)__double2loint(v[i].x);
-    r[4 * i + 1] = (unsigned)__double2hiint(v[i].x);
-    r[4 * i + 2] = (unsigned)__double2loint(v[i].y);
-    r[4 * i + 3] = (unsigned)__double2hiint(v[i].y);
-  }
-}
-__device__ __forceinline__ void unpack4(const unsigned (&r)[16], cd* v) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    v[i] = cd{__hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2])};
-}
 
-// ABL (lab only, results are wrong when != 0): 1 = no epilogue math, 2 = no global loads / conversions,
-// 4 = no CTA barriers in the frame loop, 8 = no shared-memory exchanges
-//      16 = no F2F on the inputs (bit reinterpretation), 32 = constant window (no window loads)
-// TW: where the 15 per-thread pass-1 twiddles live: 0 = registers (60), 1 = two-level (W^{tid j} x W^{4 tid m},
-//     24 registers, +36 FP64 instructions per frame), 2 = tensor memory (tcgen05.st once, tcgen05.ld per frame)
-// SR (needs TW == 2, hop == 512): per-thread ring of the 16 (target, est) samples of a frame, converted to float64,
-//     in tensor memory; consecutive interior frames load only their 4 new samples per signal from global memory
-template <int FIXED, int ABL = 0, int TW = 0, int MINB = 3, int SR = 0>
-__global__ void __launch_bounds__(kV2Threads, MINB)
+template <int FIXED, bool RING>
+__global__ void __launch_bounds__(kV2Threads, 4)
 k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __restrict__ tgt,
                     const long long* __restrict__ offsets, const int* __restrict__ item_start,
                     const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
                     double* __restrict__ partials, float* __restrict__ spec_e,
                     float* __restrict__ spec_t, const long long* __restrict__ spec_off) {
   constexpr int N = 2048, F = 1025, NW = kV2Threads / 32;
+  constexpr int kTmemCols = RING ? 128 : 64;  // [0, 60) twiddles, [64, 128) sample ring
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* const buf = reinterpret_cast<cd*>(smem_raw);                                // N + N/8 slots
   float2* const edge_raw = reinterpret_cast<float2*>(smem_raw);  // edge frames stage N raw pairs inside buf
@@ -91,6 +46,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
   __shared__ __align__(16) cd tw2[15 * 8];
   __shared__ float lsd_part[kMaxChunk][NW];
   __shared__ double red[NW][kPartials];
+  __shared__ unsigned tmem_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hop = P.hop;
@@ -102,44 +58,21 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
     spec_t = nullptr;
   }
 
-  // per-thread constants
-  cd tw1[TW == 0 ? 15 : 6];
-  unsigned tmem_base = 0;
-  __shared__ unsigned tmem_slot;
-  if (TW == 0) {
+  // per-thread constants: pass-1 twiddles W^{tid q}, q = 1..15, into this thread's TMEM lane
+  const unsigned tmem_base = tmem_alloc<kTmemCols>(&tmem_slot, warp);
 #pragma unroll
-    for (int q = 1; q < 16; ++q) tw1[q - 1] = P.tw[tid * q];
-  } else if (TW == 1) {
+  for (int c = 0; c < 4; ++c) {
+    cd w4[4];
 #pragma unroll
-    for (int j = 1; j < 4; ++j) {
-      tw1[j - 1] = P.tw[tid * j];          // A[j] = W^{tid j}
-      tw1[2 + j] = P.tw[(4 * tid * j) & 2047];  // B[m] = W^{4 tid m}
+    for (int i = 0; i < 4; ++i) {
+      const int q = 4 * c + i + 1;
+      w4[i] = q < 16 ? P.tw[tid * q] : cd{0.0, 0.0};
     }
-  } else {
-    // TMEM as a per-thread twiddle store: 64 columns (60 used) x 128 lanes; warp w owns lanes 32w..32w+31
-    if (warp == 0) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-          (unsigned)__cvta_generic_to_shared(&tmem_slot)), "n"(SR ? 128 : 64) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tmem_base = tmem_slot + ((unsigned)(warp * 32) << 16);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      cd w4[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int q = 4 * c + i + 1;
-        w4[i] = q < 16 ? P.tw[tid * q] : cd{0.0, 0.0};
-      }
-      unsigned r[16];
-      pack4(w4, r);
-      tmem_st16(tmem_base + 16 * c, r);
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    unsigned r[16];
+    tmem_pack4(w4, r);
+    tmem_st16(tmem_base + 16 * c, r);
   }
+  tmem_wait_st();
   if (tid < 120) tw2[tid] = P.tw[16 * (tid & 7) * ((tid >> 3) + 1)];  // tw2[(q-1)*8 + j] = W_128^{jq}
   int ia, ib;
   v2_thread_butterflies(tid, &ia, &ib);
@@ -168,9 +101,8 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
     float* pend_t = nullptr;
     float* pend_e = nullptr;
 
-    double abl_c = 1e-3 * tid;
-    long long ring_next = -1;  // SR: frame whose 12 older sample blocks sit in the tensor-memory ring
-    float pre_t[4], pre_e[4];  // SR == 2: that frame's 4 new samples per signal, loaded one frame ahead
+    long long ring_next = -1;  // RING: frame whose 12 older sample blocks sit in the tensor-memory ring
+    float pre_t[4], pre_e[4];  // RING: that frame's 4 new samples per signal, loaded one frame ahead
 #pragma unroll
     for (int i = 0; i < 4; ++i) pre_t[i] = pre_e[i] = 0.f;
     for (int fi = 0; fi < nf; ++fi) {
@@ -178,42 +110,38 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       const long long start = f * hop - N / 2;
       cd v[16];
       // ---- pass 1: load + window, radix-16, twiddle, store
-      if (ABL & 2) {
-        abl_c += 1e-3;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = cd{fma(abl_c, (double)r, 1.0), fma(abl_c, -(double)r, abl_c)};
-      } else if (start >= 0 && start + N <= L) {
+      if (start >= 0 && start + N <= L) {
         const float* pt = xt + start + tid;
         const float* pe = xe + start + tid;
-        if (SR) {
-          // ring chunk of sample block r (4 blocks = 16 columns per chunk): (f + 2 + r / 4) mod 4
+        if (RING) {
+          // sample block r of frame f is global block 4 f - 8 + r (blocks of 128 samples); it lives in ring
+          // chunk (f + 2 + r / 4) mod 4 (4 blocks x (target, est) x float64 = 16 columns per chunk)
           const unsigned ring = tmem_base + 64;
           const int c0 = (int)((f + 2) & 3);
           if (ring_next == f) {
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // the previous frame's ring stores
+            tmem_wait_st();  // the previous frame's ring stores
             unsigned r0[16], r1[16], r2[16], r3[16];
             tmem_ld16(ring + 16 * ((c0 + 0) & 3), r0);
             tmem_ld16(ring + 16 * ((c0 + 1) & 3), r1);
             tmem_ld16(ring + 16 * ((c0 + 2) & 3), r2);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              v[12 + i] = (SR == 2) ? cd{(double)pre_t[i], (double)pre_e[i]}
-                                    : cd{(double)__ldg(pt + 128 * (12 + i)), (double)__ldg(pe + 128 * (12 + i))};
-            pack4(v + 12, r3);
+              v[12 + i] = cd{(double)pre_t[i], (double)pre_e[i]};
+            tmem_pack4(v + 12, r3);
             tmem_st16(ring + 16 * ((c0 + 3) & 3), r3);
             tmem_wait_ld(r0);
             tmem_pin(r1);
             tmem_pin(r2);
-            unpack4(r0, v);
-            unpack4(r1, v + 4);
-            unpack4(r2, v + 8);
+            tmem_unpack4(r0, v);
+            tmem_unpack4(r1, v + 4);
+            tmem_unpack4(r2, v + 8);
           } else {
 #pragma unroll
             for (int r = 0; r < 16; ++r) v[r] = cd{(double)__ldg(pt + 128 * r), (double)__ldg(pe + 128 * r)};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               unsigned rr[16];
-              pack4(v + 4 * k, rr);
+              tmem_pack4(v + 4 * k, rr);
               tmem_st16(ring + 16 * ((c0 + k) & 3), rr);
             }
           }
@@ -225,14 +153,10 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
           }
         } else {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const double w = (ABL & 32) ? 0.5 : __ldg(P.win_half + tid + 128 * r);
-          if (ABL & 16)
-            v[r] = cd{w * __hiloint2double(__float_as_int(__ldg(pt + 128 * r)), 0),
-                      w * __hiloint2double(__float_as_int(__ldg(pe + 128 * r)), 0)};
-          else
+          for (int r = 0; r < 16; ++r) {
+            const double w = __ldg(P.win_half + tid + 128 * r);
             v[r] = cd{w * (double)__ldg(pt + 128 * r), w * (double)__ldg(pe + 128 * r)};
-        }
+          }
         }
         if (tid < 32) {
           // next frame's new samples: [start + N, start + N + hop) of both signals, one 128 B line per lane
@@ -257,16 +181,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
         }
       }
       bfly16<false>(v);
-      if (TW == 0) {
-#pragma unroll
-        for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw1[q - 1]);
-      } else if (TW == 1) {
-#pragma unroll
-        for (int q = 1; q < 16; ++q) {
-          if (q & 3) v[q] = cmul(v[q], tw1[(q & 3) - 1]);
-          if (q >> 2) v[q] = cmul(v[q], tw1[2 + (q >> 2)]);
-        }
-      } else {
+      {  // twiddles from tensor memory, four chunks of four, the next chunk in flight while one is applied
         unsigned r[2][16];
         tmem_ld16(tmem_base, r[0]);
 #pragma unroll
@@ -274,7 +189,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
           tmem_wait_ld(r[c & 1]);
           if (c < 3) tmem_ld16(tmem_base + 16 * (c + 1), r[(c + 1) & 1]);
           cd w4[4];
-          unpack4(r[c & 1], w4);
+          tmem_unpack4(r[c & 1], w4);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int q = 4 * c + i + 1;
@@ -284,7 +199,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       }
       // the previous frame's pass-3 loads must be done before buf is overwritten; placed here (after
       // this frame's loads and butterfly) the barrier finds every warp long past that point
-      if (!(ABL & 4)) __syncthreads();
+      __syncthreads();
       if (pend_t) {  // coalesced copy-out of the previous frame's magnitude rows (all epilogues are done)
         for (int k = tid; k < F; k += kV2Threads) {
           pend_t[k] = row_t[k + (k >> 4)];
@@ -292,11 +207,9 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
         }
         pend_t = nullptr;
       }
-      if (!(ABL & 8)) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
-      }
-      if (SR == 2) {
+      for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
+      if (RING) {
         const long long ns = start + hop;  // the next frame of this item, if it is an interior one
         if (fi + 1 < nf && start >= 0 && ns + N <= L) {
 #pragma unroll
@@ -306,31 +219,22 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
           }
         }
       }
-      if (!(ABL & 4)) __syncthreads();
+      __syncthreads();
       // ---- pass 2: sub-transforms of length 128 (stride 8)
-      if (!(ABL & 8)) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = b2[9 * r];
-      }
+      for (int r = 0; r < 16; ++r) v[r] = b2[9 * r];
       bfly16<false>(v);
-      if (!(ABL & 8)) {
-        b2[0] = v[0];
+      b2[0] = v[0];
 #pragma unroll
-        for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
-      } else {
-#pragma unroll
-        for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], t2[(q - 1) * 8]);
-      }
-      if (!(ABL & 4)) __syncthreads();
+      for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
+      __syncthreads();
       // ---- pass 3: two radix-8 butterflies (a and its Hermitian partner b), no twiddles
       cd* a = v;
       cd* b = v + 8;
-      if (!(ABL & 8)) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          a[r] = b3a[r];
-          b[r] = b3b[r];
-        }
+      for (int r = 0; r < 8; ++r) {
+        a[r] = b3a[r];
+        b[r] = b3b[r];
       }
       bfly8<false>(a);
       bfly8<false>(b);
@@ -339,11 +243,6 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
       float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
       auto emit = [&](int k, cd zk, cd zn) {
-        if (ABL & 1) {  // keep the four un-packing additions, drop conversions / float32 / MUFU work
-          s_et += (zk.x + zn.x) + (zk.y - zn.y);
-          s_tt += (zk.y + zn.y) + (zn.x - zk.x);
-          return;
-        }
         // T = (Z[k] + conj Z[N-k]) / 2,  E = (Z[k] - conj Z[N-k]) / (2i); the 1/2 is in the window.
         // complex64 rounding as librosa stores it, then float32 arithmetic as torch runs it; the
         // special functions are the hardware approximations (MUFU sqrt / rcp / lg2, <= 2 ulp), well
@@ -435,11 +334,8 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
     }
     __syncthreads();
   }
-  if (TW == 2) {
-    __syncthreads();
-    if (warp == 0)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "n"(SR ? 128 : 64) : "memory");
-  }
+  __syncthreads();
+  tmem_free<kTmemCols>(&tmem_slot, warp);
 }
 
 

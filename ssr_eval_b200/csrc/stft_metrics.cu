@@ -27,7 +27,6 @@
 #include "k1_common.cuh"
 #include "k1_generic.cuh"
 #include "k1_2048.cuh"
-#include "k1_2048s.cuh"
 #include "k1_pfa.cuh"
 #include "k2_ssim.cuh"
 
@@ -75,18 +74,6 @@ static bool force_generic_k1() {
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
-}
-
-// lab switches (tools/k1_lab.py), read on every launch: SSR_K1_VARIANT = 0 production kernel,
-// 1 = phase-staggered kernel, 100 + ABL = ablation of the production kernel (wrong results, timing only);
-// SSR_K1_EXTRA_SMEM = bytes of extra dynamic shared memory (limits the CTAs per SM)
-static int k1_variant() {
-  const char* e = getenv("SSR_K1_VARIANT");
-  return e ? atoi(e) : 0;
-}
-static size_t k1_extra_smem() {
-  const char* e = getenv("SSR_K1_EXTRA_SMEM");
-  return e ? (size_t)atol(e) : 0;
 }
 
 struct WsLayout {
@@ -220,6 +207,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     int gp = sms * 2;
     if (gp > w.n_items) gp = w.n_items;
     const bool store = spec_e || spec_t;
+    const bool ring = plan->hop == 512;  // TMEM sample ring: the hop has to be 4 blocks of 128 samples
     const bool lsd_only = !store && (flags & 7u) == 1u;
     const int nq = (plan->pdev.P + 127) / 128;
     TimingState& tm = timing();
@@ -257,7 +245,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     return SSR_OK;
   }
   if (!plan->bluestein && plan->logM == 11 && !force_generic_k1()) {
-    int g2 = sms * 3;
+    int g2 = sms * 4;  // 4 CTAs (16 warps) per SM: 128 registers, 50 KB shared memory, 64-128 TMEM columns each
     if (g2 > w.n_items) g2 = w.n_items;
     TimingState& tm = timing();
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -274,84 +262,16 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     const unsigned m3 = flags & 7u;
     const size_t smem2 = sizeof(cd) * (2048 + 256) + sizeof(float) * 2 * 1104;
     const bool store = spec_e || spec_t;
+    const bool ring = plan->hop == 512;  // TMEM sample ring: the hop has to be 4 blocks of 128 samples
     const int fixed = (!store && m3 == 1u) ? 1 : ((!store && m3 == 7u) ? 7 : ((spec_e && spec_t && m3 == 7u) ? 15 : -1));
-    if (g2 > sms * 3) g2 = sms * 3;
 #define SSR_V2_LAUNCH(FX)                                                                           \
   do {                                                                                              \
-    auto kern = k_stft_metrics_2048<FX>;                                                            \
+    auto kern = ring ? k_stft_metrics_2048<FX, true> : k_stft_metrics_2048<FX, false>;              \
     SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
     kern<<<g2, kV2Threads, smem2, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
                                         w.chunk, flags, partials, spec_e, spec_t, spec_off);        \
   } while (0)
-    const int variant = k1_variant();
-    if (variant == 1 && fixed > 0) {
-      const size_t smem_s = (size_t)kSG * sizeof(cd) * (2048 + 256) + (fixed == 15 ? sizeof(float) * kSG * 2 * 1104 : 0);
-      int gs = sms;
-      if (gs * kSG > w.n_items) gs = (w.n_items + kSG - 1) / kSG;
-#define SSR_V2S_LAUNCH(FX)                                                                          \
-  do {                                                                                              \
-    auto kern = k_stft_metrics_2048s<FX>;                                                           \
-    SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); \
-    kern<<<gs, kV2Threads * kSG, smem_s, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
-                                               w.chunk, flags, partials, spec_e, spec_t, spec_off); \
-  } while (0)
-      if (fixed == 1) SSR_V2S_LAUNCH(1);
-      else if (fixed == 7) SSR_V2S_LAUNCH(7);
-      else SSR_V2S_LAUNCH(15);
-#undef SSR_V2S_LAUNCH
-    } else if (variant >= 100 && fixed == 1) {
-      const size_t smem_a = smem2 + k1_extra_smem();
-#define SSR_V2A_LAUNCH(AB)                                                                          \
-  do {                                                                                              \
-    auto kern = k_stft_metrics_2048<1, AB>;                                                         \
-    SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)); \
-    kern<<<g2, kV2Threads, smem_a, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
-                                         w.chunk, flags, partials, spec_e, spec_t, spec_off);       \
-  } while (0)
-      switch (variant - 100) {
-        case 0: SSR_V2A_LAUNCH(0); break;
-        case 1: SSR_V2A_LAUNCH(1); break;
-        case 2: SSR_V2A_LAUNCH(2); break;
-        case 3: SSR_V2A_LAUNCH(3); break;
-        case 4: SSR_V2A_LAUNCH(4); break;
-        case 8: SSR_V2A_LAUNCH(8); break;
-        case 12: SSR_V2A_LAUNCH(12); break;
-        case 16: SSR_V2A_LAUNCH(16); break;
-        case 32: SSR_V2A_LAUNCH(32); break;
-        case 48: SSR_V2A_LAUNCH(48); break;
-        case 15: SSR_V2A_LAUNCH(15); break;
-        default: return fail(SSR_ERR_INVALID, "unknown SSR_K1_VARIANT ablation");
-      }
-#undef SSR_V2A_LAUNCH
-    } else if (variant >= 2 && variant <= 9) {
-#define SSR_V2T_LAUNCH(FX, TWV, MB, SRV)                                                            \
-  do {                                                                                              \
-    auto kern = k_stft_metrics_2048<FX, 0, TWV, MB, SRV>;                                           \
-    int gt = sms * MB;                                                                              \
-    if (gt > w.n_items) gt = w.n_items;                                                             \
-    SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-    kern<<<gt, kV2Threads, smem2, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
-                                        w.chunk, flags, partials, spec_e, spec_t, spec_off);        \
-  } while (0)
-#define SSR_V2T_FX(TWV, MB, SRV)                                                                    \
-  do {                                                                                              \
-    if (fixed == 1) SSR_V2T_LAUNCH(1, TWV, MB, SRV);                                                \
-    else if (fixed == 7) SSR_V2T_LAUNCH(7, TWV, MB, SRV);                                           \
-    else if (fixed == 15) SSR_V2T_LAUNCH(15, TWV, MB, SRV);                                         \
-    else SSR_V2T_LAUNCH(-1, TWV, MB, SRV);                                                          \
-  } while (0)
-      if (variant >= 6 && plan->hop != 512) return fail(SSR_ERR_INVALID, "sample-ring variants need hop 512");
-      if (variant == 2) SSR_V2T_LAUNCH(1, 1, 3, 0);       // two-level twiddles, 3 CTAs/SM
-      else if (variant == 3) SSR_V2T_LAUNCH(1, 1, 4, 0);  // two-level twiddles, 4 CTAs/SM
-      else if (variant == 4) SSR_V2T_FX(2, 3, 0);  // TMEM twiddles, 3 CTAs/SM
-      else if (variant == 5) SSR_V2T_FX(2, 4, 0);  // TMEM twiddles, 4 CTAs/SM
-      else if (variant == 6) SSR_V2T_LAUNCH(1, 2, 3, 1);  // TMEM twiddles + TMEM sample ring, 3 CTAs/SM
-      else if (variant == 7) SSR_V2T_LAUNCH(1, 2, 4, 1);  // TMEM twiddles + TMEM sample ring, 4 CTAs/SM
-      else if (variant == 8) SSR_V2T_FX(2, 3, 2);  // + new samples loaded one frame ahead, 3 CTAs/SM
-      else SSR_V2T_FX(2, 4, 2);                    // + new samples loaded one frame ahead, 4 CTAs/SM
-#undef SSR_V2T_FX
-#undef SSR_V2T_LAUNCH
-    } else if (fixed == 1) SSR_V2_LAUNCH(1);
+    if (fixed == 1) SSR_V2_LAUNCH(1);
     else if (fixed == 7) SSR_V2_LAUNCH(7);
     else if (fixed == 15) SSR_V2_LAUNCH(15);
     else SSR_V2_LAUNCH(-1);

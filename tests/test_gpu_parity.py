@@ -412,3 +412,23 @@ def test_sosfiltfilt_vs_scipy():
     with pytest.raises(ValueError):
         sosfiltfilt_batch(sos, [waves[0][:27]])
     print(f"sosfiltfilt: {n_exact}/12 single-signal cases bit-exact vs scipy")
+
+
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (2048, 441), (2229, 480), (1024, 256)])
+def test_repeatable_under_workspace_poisoning(engines, n_fft, hop):
+    """All four metrics of a ragged batch (edge frames, utterances too short for SSIM) must not depend on
+    what the caller-provided workspace held before the call: every spectrogram row, partial sum and
+    SSIM tile the later kernels read has to be written by this call.  Bit-identical across poisons."""
+    rng = np.random.default_rng(3)
+    lens = [int(x) for x in rng.integers(3000, 60000, size=40)] + [2049, 1025, 100000]
+    tgt = [(0.1 * rng.standard_normal(n)).astype(np.float32) for n in lens]
+    est = [(0.7 * t + 1e-2 * rng.standard_normal(len(t))).astype(np.float32) for t in tgt]
+    eng = engines(n_fft, hop)
+    ref = eng.metrics(est, tgt, N.METRIC_ALL)
+    short = np.array([eng.num_frames(n) < 7 for n in lens])
+    assert np.isnan(ref[short, 3]).all() and np.isfinite(ref[~short]).all() and np.isfinite(ref[:, :3]).all()
+    for poison in (0xFF, 0x7F, 0x3C):
+        eng._ws.buf.fill_(poison)
+        torch.cuda.synchronize()
+        got = eng.metrics(est, tgt, N.METRIC_ALL)
+        assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(ref, nan=-1.0)), poison
