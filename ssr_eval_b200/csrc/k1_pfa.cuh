@@ -1,7 +1,9 @@
 // k1_pfa.cuh -- K1, PFA kernel for n_fft = R * P (R Bluestein sub-transforms on the 2048-point machinery).
 #pragma once
+#include <type_traits>
 #include "k1_common.cuh"
 #include "k1_map.cuh"
+#include "tmem.cuh"
 
 namespace ssr {
 
@@ -14,13 +16,14 @@ namespace ssr {
 // than the generic Bluestein kernel).  NQ = ceil(P / 128): pass-1 inputs / pass-3' outputs beyond
 // NQ are structurally zero / unused and are pruned at compile time.
 // ---------------------------------------------------------------------------------------------
-// 2 CTAs/SM (255 registers): the Bluestein filter values of the thread's two butterflies live in
-// registers and the samples + window*chirp factors of the NEXT sub-transform are fetched into registers
-// one sub-transform ahead -- the tables (103 KB) do not fit the L1 left beside the CTAs' shared memory,
-// so every table load is an L2 round trip that has to be hidden in software (measured: 21.6k -> 25.7k
-// pairs/s against the 3-CTA version that loaded in place).
+// 3 CTAs/SM (168 registers): the pass-1 twiddles and the Bluestein filter values of the thread's two
+// butterflies live in tensor memory (tmem.cuh), and the samples + window*chirp factors of the NEXT
+// sub-transform are fetched into registers one sub-transform ahead -- the tables (103 KB) do not fit the L1
+// left beside the CTAs' shared memory, so every table load is an L2 round trip that has to be hidden in
+// software.  Measured (LSD only, 256 pairs x 5 s): 21.6k pairs/s (3 CTAs, loads in place) -> 25.7k (2 CTAs,
+// 255 registers, constants in registers, software pipeline) -> 31.2k (3 CTAs, constants in TMEM, pipeline).
 template <int NQ, int FIXED>
-__global__ void __launch_bounds__(kV2Threads, 2)
+__global__ void __launch_bounds__(kV2Threads, 3)
 k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restrict__ tgt,
                    const long long* __restrict__ offsets, const int* __restrict__ item_start,
                    const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
@@ -47,9 +50,7 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
     spec_t = nullptr;
   }
 
-  cd tw1[15];
-#pragma unroll
-  for (int q = 1; q < 16; ++q) tw1[q - 1] = D.tw[tid * q];
+  __shared__ unsigned tmem_slot;
   if (tid < 120) tw2[tid] = D.tw[16 * (tid & 7) * ((tid >> 3) + 1)];
   if (tid < R * R) wr_s[tid] = D.wr[tid];
   int ia, ib;
@@ -62,14 +63,47 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
   const cd* const t2 = tw2 + j2;
   __syncthreads();
 
-  cd fa[8], fb[8];  // Bluestein filter at this thread's 16 slots
-  {
+  // Per-thread constants live in TENSOR MEMORY, this thread's lane: columns [0, 60) the pass-1 twiddles
+  // W^{tid q}, [64, 96) the Bluestein filter at butterfly a's 8 slots, [96, 128) at butterfly b's -- 124
+  // registers' worth that the register file no longer has to hold (written once with tcgen05.st).
+  const unsigned tmem_base = tmem_alloc<128>(&tmem_slot, warp);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      fa[q] = D.bfilt[8 * ia + q];
-      fb[q] = D.bfilt[8 * ib + q];
+  for (int c = 0; c < 8; ++c) {
+    cd w4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (c < 4) {
+        const int q = 4 * c + i + 1;
+        w4[i] = q < 16 ? D.tw[tid * q] : cd{0.0, 0.0};
+      } else {
+        const int q = 4 * (c & 1) + i;
+        w4[i] = D.bfilt[8 * (c < 6 ? ia : ib) + q];
+      }
     }
+    unsigned r[16];
+    tmem_pack4(w4, r);
+    tmem_st16(tmem_base + 16 * c, r);
   }
+  tmem_wait_st();
+  // v[q] *= W^{tid q} (or its conjugate), q = 1..15: four chunks of four twiddles from tensor memory, the next
+  // chunk in flight while one is applied
+  auto apply_tw1 = [&](cd* v, auto conj_tag) {
+    constexpr bool CONJ = decltype(conj_tag)::value;
+    unsigned r[2][16];
+    tmem_ld16(tmem_base, r[0]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      tmem_wait_ld(r[c & 1]);
+      if (c < 3) tmem_ld16(tmem_base + 16 * (c + 1), r[(c + 1) & 1]);
+      cd w4[4];
+      tmem_unpack4(r[c & 1], w4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = 4 * c + i + 1;
+        if (q < 16) v[q] = CONJ ? cmul_conj(v[q], w4[i]) : cmul(v[q], w4[i]);
+      }
+    }
+  };
 
   auto combine = [&](int kap) {  // Z[kap] = sum_r W_R^{r m} Y_r[k], kap = k + P m
     int m = 0;
@@ -140,8 +174,7 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
         if (r + 1 < R) fetch_inputs(f, r + 1);
         else if (fi + 1 < nf) fetch_inputs(f + 1, 0);
         bfly16<false>(v);
-#pragma unroll
-        for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw1[q - 1]);
+        apply_tw1(v, std::false_type{});
         __syncthreads();  // previous sub-transform's last loads are done
 #pragma unroll
         for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
@@ -162,12 +195,20 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
           a[q] = b3a[q];
           b[q] = b3b[q];
         }
-        bfly8<false>(a);
-        bfly8<false>(b);
+        {
+          unsigned r[2][16];
+          tmem_ld16(tmem_base + 64, r[0]);  // the filter values arrive while the butterflies run
+          bfly8<false>(a);
+          bfly8<false>(b);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          a[q] = cmul(a[q], fa[q]);
-          b[q] = cmul(b[q], fb[q]);
+          for (int c = 0; c < 4; ++c) {
+            tmem_wait_ld(r[c & 1]);
+            if (c < 3) tmem_ld16(tmem_base + 64 + 16 * (c + 1), r[(c + 1) & 1]);
+            cd w4[4];
+            tmem_unpack4(r[c & 1], w4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[4 * c + i] = cmul(v[4 * c + i], w4[i]);  // v = a[0..7], b[0..7]
+          }
         }
         bfly8<true>(a);
         bfly8<true>(b);
@@ -186,9 +227,9 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
         for (int q = 0; q < 16; ++q) b2[9 * q] = v[q];
         __syncthreads();
         // ---- inverse pass 3 -> conv[k], k = tid + 128 q; Y_r[k] = conv[k] * chirp[k] * W_N^{rk}
-        v[0] = b1[0];
 #pragma unroll
-        for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b1[144 * q], tw1[q - 1]);
+        for (int q = 0; q < 16; ++q) v[q] = b1[144 * q];
+        apply_tw1(v, std::true_type{});
         bfly16<true>(v);
         cd* Yr = Yx + r * P;
         if (r == R - 1) {
@@ -263,6 +304,8 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
     }
     __syncthreads();
   }
+  __syncthreads();
+  tmem_free<128>(&tmem_slot, warp);
 }
 
 

@@ -204,10 +204,9 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   if (grid > w.n_items) grid = w.n_items;
   if (plan->pfa && !force_generic_k1()) {
     const size_t smem_p = sizeof(cd) * (2048 + 256) + sizeof(cd) * (size_t)(plan->n_fft - plan->pdev.P);
-    int gp = sms * 2;
+    int gp = sms * 3;
     if (gp > w.n_items) gp = w.n_items;
     const bool store = spec_e || spec_t;
-    const bool ring = plan->hop == 512;  // TMEM sample ring: the hop has to be 4 blocks of 128 samples
     const bool lsd_only = !store && (flags & 7u) == 1u;
     const int nq = (plan->pdev.P + 127) / 128;
     TimingState& tm = timing();
