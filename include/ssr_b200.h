@@ -79,6 +79,16 @@ int ssr_stft_metrics_batched(const ssr_stft_plan* plan, const float* est_dev, co
                              unsigned flags, double* out_dev, void* workspace_dev,
                              size_t workspace_bytes, void* stream);
 
+/* Same, for a float64 ESTIMATE batch (target stays float32).  The reference's zero-phase IIR low-pass filters
+ * (ssr_eval/lowpass.py:94-131, scipy sosfiltfilt) return float64, an identity-like testee hands that to
+ * AudioMetrics.evaluation (ssr_eval/eval.py:138-151), and librosa / torch then keep the estimate's spectrum,
+ * magnitude and every formula that touches it in float64 (metrics.py:26-30, 109-121): only the target is
+ * rounded to complex64 / float32.  Same workspace as ssr_stft_metrics_batched. */
+int ssr_stft_metrics_batched_f64est(const ssr_stft_plan* plan, const double* est_dev, const float* tgt_dev,
+                                    const int64_t* offsets_host, const int64_t* offsets_dev, int n_pairs,
+                                    unsigned flags, double* out_dev, void* workspace_dev,
+                                    size_t workspace_bytes, void* stream);
+
 /* Magnitude spectrogram only (AudioMetrics.wav_to_spectrogram, metrics.py:26-30) of one ragged
  * batch: spec_dev receives, utterance after utterance, T_i x F float32 row-major (F = n_fft/2+1).
  * Needs the same workspace as ssr_stft_metrics_batched with flags = 0. */
@@ -105,6 +115,16 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
                               const int64_t* in_offsets_host, const int64_t* in_offsets_dev,
                               float* y_dev, const int64_t* out_offsets_host,
                               const int64_t* out_offsets_dev, int n, void* stream);
+
+/* float64 form (taps, input and output float64): what librosa.resample(res_type="polyphase") does when the
+ * testee hands back a float64 waveform (scipy.signal.resample_poly keeps the input dtype, eval.py:144-150).
+ * A plan is either float32 or float64; mixing them is SSR_ERR_INVALID. */
+int ssr_resample_plan_create_f64(ssr_resample_plan** plan, int up, int down, const double* taps_host,
+                                 int n_taps);
+int ssr_resample_poly_batched_f64(const ssr_resample_plan* plan, const double* x_dev,
+                                  const int64_t* in_offsets_host, const int64_t* in_offsets_dev,
+                                  double* y_dev, const int64_t* out_offsets_host,
+                                  const int64_t* out_offsets_dev, int n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4: STFT hard low-pass = stft_hard_lowpass_v0 (ssr_eval/lowpass.py:17-28) through

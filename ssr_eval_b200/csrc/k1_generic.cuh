@@ -1,5 +1,6 @@
 // k1_generic.cuh -- K1, generic kernel: any power-of-two n_fft (direct) or Bluestein with M <= 8192 (radix-8/4 in-place FFT).
 #pragma once
+#include <type_traits>
 #include "k1_common.cuh"
 
 namespace ssr {
@@ -8,10 +9,17 @@ namespace ssr {
 // K1: one CTA walks the frames of its work items; per frame:
 //   load (window folded in) -> forward FFT in shared memory [-> Bluestein filter -> inverse FFT]
 //   -> separate the two spectra -> complex64 rounding -> float32 magnitudes -> metric terms.
+//
+// ET = double: the ESTIMATE is a float64 waveform (what the reference's IIR low-pass filters hand to an
+// identity-like testee: scipy's sosfiltfilt returns float64).  librosa then keeps the estimate's spectrum
+// in complex128 / its magnitude in float64 (dtype_r2c), and every torch formula that mixes it with the
+// float32 target promotes to float64 (metrics.py:109-121).  Reproduced here: E stays float64 from the
+// waveform to the sums; only T is rounded to complex64 / float32.  (SSIM gets the float32-rounded |E|:
+// skimage would run in float64, a ~1e-7 effect against the 1e-3 tolerance.)
 // ---------------------------------------------------------------------------------------------
-template <int LOGM, bool BLUE>
+template <int LOGM, bool BLUE, typename ET>
 __global__ void __launch_bounds__(kThreads)
-k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict__ tgt,
+k_stft_metrics(StftDev P, const ET* __restrict__ est, const float* __restrict__ tgt,
                const long long* __restrict__ offsets, const int* __restrict__ item_start,
                const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
                double* __restrict__ partials, float* __restrict__ spec_e,
@@ -19,7 +27,9 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
   constexpr int M = 1 << LOGM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* buf = reinterpret_cast<cd*>(smem_raw);
-  __shared__ float lsd_part[kMaxChunk][kWarps];
+  constexpr bool E64 = sizeof(ET) == 8;
+  using LT = typename std::conditional<E64, double, float>::type;  // type of the per-frame LSD sums
+  __shared__ LT lsd_part[kMaxChunk][kWarps];
   __shared__ double red[kWarps][kPartials];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -35,7 +45,7 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
     const long long T = stft_frames(L, N, hop);
     const long long f0 = (long long)c * chunk;
     const int nf = (int)min((long long)chunk, T - f0);
-    const float* xe = est + off;
+    const ET* xe = est + off;
     const float* xt = tgt + off;
     double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
 
@@ -71,7 +81,7 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
         __syncthreads();
       }
       // ---- epilogue over the F = n_fft/2+1 bins
-      float lsd_acc = 0.f;
+      LT lsd_acc = 0;
       float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
       float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
       for (int k = tid; k < F; k += kThreads) {
@@ -86,8 +96,31 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
         }
         // T = (Z[k] + conj Z[N-k]) / 2,  E = (Z[k] - conj Z[N-k]) / (2i); the 1/2 is in the window
         float tre = (float)(a.x + b.x), tim = (float)(a.y - b.y);
-        float ere = (float)(a.y + b.y), eim = (float)(b.x - a.x);
         float mt = sqrtf(tre * tre + tim * tim);
+        if (E64) {
+          const double me = hypot(a.y + b.y, b.x - a.x);  // np.abs(complex128)
+          if (st) st[k] = mt;
+          if (se) se[k] = (float)me;
+          if (want_lsd) {
+            const double den = me + 1e-12;
+            const double l = log10((double)(mt * mt) / (den * den) + 1e-12);  // target ** 2 is float32
+            lsd_acc += l * l;
+          }
+          if (want_lin) {
+            const double dt = (double)mt;
+            s_et = fma(me, dt, s_et);
+            s_tt = fma(dt, dt, s_tt);
+            s_ee = fma(me, me, s_ee);
+          }
+          if (want_log) {
+            const double le = log10(me + 1e-12), lt = (double)log10f(mt + 1e-12f);
+            l_et = fma(le, lt, l_et);
+            l_tt = fma(lt, lt, l_tt);
+            l_ee = fma(le, le, l_ee);
+          }
+          continue;
+        }
+        float ere = (float)(a.y + b.y), eim = (float)(b.x - a.x);
         float me = sqrtf(ere * ere + eim * eim);
         if (st) st[k] = mt;
         if (se) se[k] = me;
@@ -113,7 +146,7 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
         }
       }
       if (want_lsd) {
-        float w = warp_sum(lsd_acc);
+        const LT w = warp_sum(lsd_acc);
         if (lane == 0) lsd_part[fi][warp] = w;
       }
       __syncthreads();  // buf is rewritten by the next frame's load
@@ -122,10 +155,11 @@ k_stft_metrics(StftDev P, const float* __restrict__ est, const float* __restrict
     // ---- per-item reduction -> partials[item][0..7]
     double lsd_sum = 0.0;
     if (want_lsd && tid < nf) {
-      float s = 0.f;
+      LT s = 0;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) s += lsd_part[tid][w];
-      lsd_sum = (double)sqrtf(s / (float)F);  // torch.mean(dim=3) ** 0.5 in float32
+      // torch.mean(dim=3) ** 0.5 in float32 (float64 when the estimate is float64)
+      lsd_sum = E64 ? sqrt((double)s / (double)F) : (double)sqrtf((float)s / (float)F);
     }
     double v[7] = {lsd_sum, s_et, s_tt, s_ee, l_et, l_tt, l_ee};
 #pragma unroll

@@ -15,21 +15,30 @@
 
 struct ssr_resample_plan {
   int up, down, n_taps, half_len, n_pre_pad, n_pre_remove, K, device;
-  float* bank;  // [up][K]: bank[phase*K + k] = h[phase + k*up] (0 beyond n_taps)
+  int is_f64;   // 1: float64 plan (bank holds doubles), for float64 waveforms
+  void* bank;   // [up][K]: bank[phase*K + k] = h[phase + k*up] (0 beyond n_taps); float or double
 };
 
 namespace ssr {
 
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+// one output per thread; T = float (fallback for exotic ratios) or double (float64 waveforms: what
+// librosa.resample hands to scipy when a testee returns float64, eval.py:144-150)
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_resample(const float* __restrict__ x, const long long* __restrict__ in_off, float* __restrict__ y,
+k_resample(const T* __restrict__ x, const long long* __restrict__ in_off, T* __restrict__ y,
            const long long* __restrict__ out_off, int u0, int up, int down, int n_pre_pad,
-           int n_pre_remove, int K, const float* __restrict__ bank) {
+           int n_pre_remove, int K, const T* __restrict__ bank) {
   const int u = u0 + blockIdx.y;
   const long long n_out = out_off[u + 1] - out_off[u];
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_out) return;
   const long long n_in = in_off[u + 1] - in_off[u];
-  const float* xu = x + in_off[u];
+  const T* xu = x + in_off[u];
   const long long c = (j + n_pre_remove) * (long long)down - n_pre_pad;
   long long i_hi = c / up;
   long long phase = c - i_hi * up;
@@ -37,11 +46,11 @@ k_resample(const float* __restrict__ x, const long long* __restrict__ in_off, fl
     phase += up;
     i_hi -= 1;
   }
-  const float* hb = bank + phase * K;
-  float acc = 0.f;
+  const T* hb = bank + phase * K;
+  T acc = 0;
   for (int k = K - 1; k >= 0; --k) {
     long long i = i_hi - k;
-    if (i >= 0 && i < n_in) acc = __fadd_rn(acc, __fmul_rn(__ldg(xu + i), __ldg(hb + k)));
+    if (i >= 0 && i < n_in) acc = add_rn(acc, mul_rn(__ldg(xu + i), __ldg(hb + k)));
   }
   y[out_off[u] + j] = acc;
 }
@@ -121,10 +130,9 @@ k_resample_tiled(const float* __restrict__ x, const long long* __restrict__ in_o
 
 using namespace ssr;
 
-extern "C" {
 
-int ssr_resample_plan_create(ssr_resample_plan** out, int up, int down, const float* taps_host,
-                             int n_taps) {
+template <typename T>
+static int resample_plan_create(ssr_resample_plan** out, int up, int down, const T* taps_host, int n_taps) {
   if (!out) return fail(SSR_ERR_INVALID, "plan pointer is NULL");
   *out = nullptr;
   if (up < 1 || down < 1 || !taps_host || n_taps < 1 || (n_taps % 2) == 0)
@@ -137,7 +145,8 @@ int ssr_resample_plan_create(ssr_resample_plan** out, int up, int down, const fl
   p->n_pre_pad = down - p->half_len % down;
   p->n_pre_remove = (p->half_len + p->n_pre_pad) / down;
   p->K = (n_taps + up - 1) / up;
-  std::vector<float> bank((size_t)up * p->K, 0.f);
+  p->is_f64 = sizeof(T) == 8;
+  std::vector<T> bank((size_t)up * p->K, (T)0);
   for (int ph = 0; ph < up; ++ph)
     for (int k = 0; k < p->K; ++k) {
       long long q = ph + (long long)k * up;
@@ -145,9 +154,9 @@ int ssr_resample_plan_create(ssr_resample_plan** out, int up, int down, const fl
     }
   p->bank = nullptr;
   cudaError_t e = cudaGetDevice(&p->device);
-  if (e == cudaSuccess) e = cudaMalloc(&p->bank, bank.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&p->bank, bank.size() * sizeof(T));
   if (e == cudaSuccess)
-    e = cudaMemcpy(p->bank, bank.data(), bank.size() * sizeof(float), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(p->bank, bank.data(), bank.size() * sizeof(T), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     if (p->bank) cudaFree(p->bank);
     delete p;
@@ -155,6 +164,18 @@ int ssr_resample_plan_create(ssr_resample_plan** out, int up, int down, const fl
   }
   *out = p;
   return SSR_OK;
+}
+
+extern "C" {
+
+int ssr_resample_plan_create(ssr_resample_plan** out, int up, int down, const float* taps_host,
+                             int n_taps) {
+  return resample_plan_create<float>(out, up, down, taps_host, n_taps);
+}
+
+int ssr_resample_plan_create_f64(ssr_resample_plan** out, int up, int down, const double* taps_host,
+                                 int n_taps) {
+  return resample_plan_create<double>(out, up, down, taps_host, n_taps);
 }
 
 int ssr_resample_plan_destroy(ssr_resample_plan* plan) {
@@ -170,10 +191,41 @@ int64_t ssr_resample_out_len(const ssr_resample_plan* plan, int64_t n_in) {
   return (int64_t)(t / plan->down + (t % plan->down ? 1 : 0));
 }
 
+int ssr_resample_poly_batched_f64(const ssr_resample_plan* plan, const double* x_dev,
+                                  const int64_t* in_offsets_host, const int64_t* in_offsets_dev,
+                                  double* y_dev, const int64_t* out_offsets_host,
+                                  const int64_t* out_offsets_dev, int n, void* stream) {
+  if (!plan || !x_dev || !y_dev || !in_offsets_host || !in_offsets_dev || !out_offsets_host ||
+      !out_offsets_dev || n < 1)
+    return fail(SSR_ERR_INVALID, "ssr_resample_poly_batched_f64: bad argument");
+  if (!plan->is_f64) return fail(SSR_ERR_INVALID, "float32 plan used with float64 data");
+  long long max_out = 0;
+  for (int u = 0; u < n; ++u) {
+    long long n_in = in_offsets_host[u + 1] - in_offsets_host[u];
+    long long n_out = out_offsets_host[u + 1] - out_offsets_host[u];
+    if (n_out != ssr_resample_out_len(plan, n_in))
+      return fail(SSR_ERR_INVALID, "output offsets do not match ceil(n_in*up/down)");
+    if (n_out > max_out) max_out = n_out;
+  }
+  if (max_out == 0) return SSR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int u0 = 0; u0 < n; u0 += 32768) {
+    int nu = n - u0 < 32768 ? n - u0 : 32768;
+    dim3 grid((unsigned)((max_out + 255) / 256), nu);
+    k_resample<double><<<grid, 256, 0, st>>>(x_dev, reinterpret_cast<const long long*>(in_offsets_dev), y_dev,
+                                             reinterpret_cast<const long long*>(out_offsets_dev), u0, plan->up,
+                                             plan->down, plan->n_pre_pad, plan->n_pre_remove, plan->K,
+                                             static_cast<const double*>(plan->bank));
+    SSR_LAUNCH_CHECK("k_resample<double>");
+  }
+  return SSR_OK;
+}
+
 int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
                               const int64_t* in_offsets_host, const int64_t* in_offsets_dev,
                               float* y_dev, const int64_t* out_offsets_host,
                               const int64_t* out_offsets_dev, int n, void* stream) {
+  if (plan && plan->is_f64) return fail(SSR_ERR_INVALID, "float64 plan used with float32 data");
   if (!plan || !x_dev || !y_dev || !in_offsets_host || !in_offsets_dev || !out_offsets_host ||
       !out_offsets_dev || n < 1)
     return fail(SSR_ERR_INVALID, "ssr_resample_poly_batched: bad argument");
@@ -198,10 +250,10 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
       const long long* oo = reinterpret_cast<const long long*>(out_offsets_dev);
       if (plan->K <= 24)
         k_resample_tiled<24, R><<<grid, TP, 0, st>>>(x_dev, io, y_dev, oo, u0, plan->up, plan->down,
-                                                     plan->n_pre_pad, plan->n_pre_remove, plan->K, plan->bank);
+                                                     plan->n_pre_pad, plan->n_pre_remove, plan->K, static_cast<const float*>(plan->bank));
       else
         k_resample_tiled<48, R><<<grid, TP, 0, st>>>(x_dev, io, y_dev, oo, u0, plan->up, plan->down,
-                                                     plan->n_pre_pad, plan->n_pre_remove, plan->K, plan->bank);
+                                                     plan->n_pre_pad, plan->n_pre_remove, plan->K, static_cast<const float*>(plan->bank));
       SSR_LAUNCH_CHECK("k_resample_tiled");
     }
     return SSR_OK;
@@ -209,10 +261,10 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
   for (int u0 = 0; u0 < n; u0 += 32768) {
     int nu = n - u0 < 32768 ? n - u0 : 32768;
     dim3 grid((unsigned)((max_out + 255) / 256), nu);
-    k_resample<<<grid, 256, 0, st>>>(x_dev, reinterpret_cast<const long long*>(in_offsets_dev), y_dev,
-                                     reinterpret_cast<const long long*>(out_offsets_dev), u0, plan->up,
-                                     plan->down, plan->n_pre_pad, plan->n_pre_remove, plan->K,
-                                     plan->bank);
+    k_resample<float><<<grid, 256, 0, st>>>(x_dev, reinterpret_cast<const long long*>(in_offsets_dev), y_dev,
+                                            reinterpret_cast<const long long*>(out_offsets_dev), u0, plan->up,
+                                            plan->down, plan->n_pre_pad, plan->n_pre_remove, plan->K,
+                                            static_cast<const float*>(plan->bank));
     SSR_LAUNCH_CHECK("k_resample");
   }
   return SSR_OK;

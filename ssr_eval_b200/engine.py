@@ -35,10 +35,10 @@ def offsets_of(lengths):
     return off
 
 
-def pack_ragged(arrays, pinned=False):
-    """Concatenate 1-D float arrays into one float32 host buffer + int64 offsets."""
+def pack_ragged(arrays, pinned=False, dtype=torch.float32):
+    """Concatenate 1-D float arrays into one float32 (or float64) host buffer + int64 offsets."""
     off = offsets_of([len(a) for a in arrays])
-    flat = torch.empty(int(off[-1]), dtype=torch.float32, pin_memory=pinned)
+    flat = torch.empty(int(off[-1]), dtype=dtype, pin_memory=pinned)
     fn = flat.numpy()
     for a, s, e in zip(arrays, off[:-1], off[1:]):
         fn[s:e] = a
@@ -91,16 +91,18 @@ class StftMetrics:
         if need == 0:
             raise N.NativeError("workspace query failed: " + (N.lib().ssr_last_error() or b"").decode())
         ws = self._ws.get(need, est_dev.device)
-        N.check(N.lib().ssr_stft_metrics_batched(self._plan, _ptr(est_dev), _ptr(tgt_dev), _np_ptr(off_np),
-                                                 _ptr(off_dev), n, flags, _ptr(out_dev), _ptr(ws),
-                                                 ws.numel(), _stream()), "ssr_stft_metrics_batched")
+        fn = N.lib().ssr_stft_metrics_batched_f64est if est_dev.dtype == torch.float64 else N.lib().ssr_stft_metrics_batched
+        N.check(fn(self._plan, _ptr(est_dev), _ptr(tgt_dev), _np_ptr(off_np), _ptr(off_dev), n, flags,
+                   _ptr(out_dev), _ptr(ws), ws.numel(), _stream()), "ssr_stft_metrics_batched")
 
     def metrics_device(self, est_dev, tgt_dev, offsets, flags=N.METRIC_ALL, offsets_dev=None, out=None):
-        """est_dev/tgt_dev: flat float32 CUDA tensors (ragged, same offsets). Returns (n,4) float64
+        """est_dev/tgt_dev: flat float32 CUDA tensors (ragged, same offsets); est_dev may be float64 (the
+        reference's float64-estimate arithmetic, see include/ssr_b200.h). Returns (n,4) float64
         CUDA tensor [lsd, log_sispec, sispec, ssim] (NaN where not requested). Asynchronous."""
         off_np = np.ascontiguousarray(offsets, dtype=np.int64)
         n = len(off_np) - 1
-        assert est_dev.is_cuda and tgt_dev.is_cuda and est_dev.dtype == torch.float32
+        assert est_dev.is_cuda and tgt_dev.is_cuda and tgt_dev.dtype == torch.float32
+        assert est_dev.dtype in (torch.float32, torch.float64)
         assert est_dev.numel() >= off_np[-1] and tgt_dev.numel() >= off_np[-1]
         dev = est_dev.device
         if offsets_dev is None:
@@ -129,11 +131,19 @@ class StftMetrics:
 
     def metrics(self, est_list, tgt_list, flags=N.METRIC_ALL):
         """Host entry: lists of 1-D float arrays (already truncated to equal length per pair).
-        Returns (n,4) float64 numpy."""
+        Returns (n,4) float64 numpy.  Pairs whose estimate is a float64 array are scored with the reference's
+        float64-estimate arithmetic (one extra launch sequence for them)."""
         assert len(est_list) == len(tgt_list) and len(est_list) > 0
         for a, b in zip(est_list, tgt_list):
             assert len(a) == len(b)
-        e_h, off = pack_ragged(est_list, pinned=True)
+        is64 = [np.asarray(a).dtype == np.float64 for a in est_list]
+        if any(is64) and not all(is64):
+            out = np.empty((len(est_list), 4), dtype=np.float64)
+            for want in (False, True):
+                idx = [i for i, f in enumerate(is64) if f == want]
+                out[idx] = self.metrics([est_list[i] for i in idx], [tgt_list[i] for i in idx], flags)
+            return out
+        e_h, off = pack_ragged(est_list, pinned=True, dtype=torch.float64 if is64[0] else torch.float32)
         t_h, _ = pack_ragged(tgt_list, pinned=True)
         e_d = e_h.cuda(non_blocking=True)
         t_d = t_h.cuda(non_blocking=True)
@@ -172,18 +182,23 @@ def resample_poly_taps(up, down, dtype=np.float32):
 
 
 class PolyphaseResampler:
-    """K3: scipy.signal.resample_poly(x, up, down) for float32 batches."""
+    """K3: scipy.signal.resample_poly(x, up, down) for float32 batches (dtype=np.float64: float64 batches --
+    scipy keeps the input dtype, so a float64 waveform is filtered with float64 taps in float64)."""
 
-    def __init__(self, up, down):
+    def __init__(self, up, down, dtype=np.float32):
         _require_cuda()
         g = gcd(int(up), int(down))
         self.up, self.down = int(up) // g, int(down) // g
         self.identity = self.up == 1 and self.down == 1
+        self.dtype = np.dtype(dtype)
+        assert self.dtype in (np.dtype(np.float32), np.dtype(np.float64))
+        self._tdtype = torch.float64 if self.dtype == np.float64 else torch.float32
         self._plan = ctypes.c_void_p()
         if not self.identity:
-            taps = np.ascontiguousarray(resample_poly_taps(self.up, self.down))
-            N.check(N.lib().ssr_resample_plan_create(ctypes.byref(self._plan), self.up, self.down,
-                                                     _np_ptr(taps), len(taps)), "ssr_resample_plan_create")
+            taps = np.ascontiguousarray(resample_poly_taps(self.up, self.down, dtype=self.dtype))
+            create = N.lib().ssr_resample_plan_create_f64 if self.dtype == np.float64 else N.lib().ssr_resample_plan_create
+            N.check(create(ctypes.byref(self._plan), self.up, self.down, _np_ptr(taps), len(taps)),
+                    "ssr_resample_plan_create")
 
     def __del__(self):
         try:
@@ -206,14 +221,15 @@ class PolyphaseResampler:
         n = len(in_off) - 1
         out_off = offsets_of([self.out_len(l) for l in np.diff(in_off)])
         out_off_dev = torch.from_numpy(out_off).to(x_dev.device)
-        y = torch.empty(int(out_off[-1]), dtype=torch.float32, device=x_dev.device)
-        N.check(N.lib().ssr_resample_poly_batched(self._plan, _ptr(x_dev), _np_ptr(in_off), _ptr(in_offsets_dev),
-                                                  _ptr(y), _np_ptr(out_off), _ptr(out_off_dev), n, _stream()),
-                "ssr_resample_poly_batched")
+        assert x_dev.dtype == self._tdtype
+        y = torch.empty(int(out_off[-1]), dtype=self._tdtype, device=x_dev.device)
+        run = N.lib().ssr_resample_poly_batched_f64 if self.dtype == np.float64 else N.lib().ssr_resample_poly_batched
+        N.check(run(self._plan, _ptr(x_dev), _np_ptr(in_off), _ptr(in_offsets_dev), _ptr(y), _np_ptr(out_off),
+                    _ptr(out_off_dev), n, _stream()), "ssr_resample_poly_batched")
         return y, out_off, out_off_dev
 
     def resample(self, wav_list):
-        x_h, off = pack_ragged(wav_list, pinned=True)
+        x_h, off = pack_ragged(wav_list, pinned=True, dtype=self._tdtype)
         y, out_off, _ = self.resample_device(x_h.cuda(non_blocking=True), off)
         yh = y.cpu().numpy()
         return [yh[s:e].copy() for s, e in zip(out_off[:-1], out_off[1:])]

@@ -143,18 +143,90 @@ class SSR_Eval_Helper:
         x, _ = load_audio(file, sr=sr)
         return self._degrade_batch([x], sr)[0]
 
+    # The reference's per-family degradation methods (eval.py:334-421), same names, arguments and keys; `file`
+    # is accepted and unused, as there.  Each one is the matching slice of _degrade_batch for one waveform.
+    def _degrade_only(self, x, sr, lowpass_filter=None, subsampling=False, fft=False):
+        lp = self.setting_lowpass_filtering
+        probe = SSR_Eval_Helper.__new__(SSR_Eval_Helper)
+        probe.setting_lowpass_filtering = None if lowpass_filter is None else dict(lp, filter=[lowpass_filter])
+        probe.setting_subsampling = self.setting_subsampling if subsampling else None
+        probe.setting_fft = self.setting_fft if fft else None
+        probe.setting_mp3_compression = None
+        return probe._degrade_batch([np.asarray(x)], sr)[0]
+
+    def lowpass_butterworth(self, file, x, sr):
+        return self._degrade_only(x, sr, lowpass_filter="butter")
+
+    def lowpass_chebyshev(self, file, x, sr):
+        return self._degrade_only(x, sr, lowpass_filter="cheby")
+
+    def lowpass_ellip(self, file, x, sr):
+        return self._degrade_only(x, sr, lowpass_filter="ellip")
+
+    def lowpass_bessel(self, file, x, sr):
+        return self._degrade_only(x, sr, lowpass_filter="bessel")
+
+    def lowpass_subsampling(self, file, x, sr):
+        return self._degrade_only(x, sr, subsampling=True)
+
+    def lowpass_stft_hard(self, file, x, sr):
+        return self._degrade_only(x, sr, fft=True)
+
+    def mp3_encoding(self, file, x, sr):
+        raise NotImplementedError("mp3 degradation needs the external sox binary (eval.py:302-325); out of scope")
+
+    # length / alignment helpers of the mp3 path (eval.py:272-300), kept for API completeness
+    def shift(self, x, shift):
+        ret = np.zeros_like(x)
+        if shift >= 0:
+            ret[:-shift] = x[shift:]  # shift == 0 raises, as in the reference (ret[:-0] is empty)
+        elif shift < 0:
+            ret[-shift:] = x[:-(-shift)]
+        return ret
+
+    def pad(self, x, y):
+        if x.shape[0] == y.shape[0]:
+            return x, y
+        if x.shape[0] > y.shape[0]:
+            cache_y = np.zeros_like(x)
+            cache_y[: y.shape[0]] = y
+            return x, cache_y
+        cache_x = np.zeros_like(y)
+        cache_x[: x.shape[0]] = x
+        return cache_x, y
+
+    def unify_length(self, x, target):
+        if x.shape[0] == target.shape[0]:
+            return x, target
+        if x.shape[0] > target.shape[0]:
+            return x[: target.shape[0]], target
+        cache_x = np.zeros_like(target)
+        cache_x[: x.shape[0]] = x
+        return cache_x, target
+
+    def cache_file_name(self, key, file, suffix=".flac"):
+        return os.path.join(os.path.dirname(file), os.path.splitext(os.path.basename(file))[0] + "_" + key + suffix)
+
     # ------------------------------------------------------------------ scoring (eval.py:128-156)
     def _resample_to_eval(self, waves):
+        """librosa.resample(processed, output_sr, evaluation_sr, res_type="polyphase") (eval.py:144-150):
+        scipy resample_poly in the waveform's own dtype (float64 stays float64), then fix_length."""
         if self.model_output_sr == self.evaluationset_sr:
             return waves
         if self._out_resampler is None:
-            self._out_resampler = PolyphaseResampler(self.evaluationset_sr, self.model_output_sr)
-        ys = self._out_resampler.resample([np.asarray(w, dtype=np.float32) for w in waves])
-        out = []
+            self._out_resampler = {}
+        out = [None] * len(waves)
         ratio = float(self.evaluationset_sr) / self.model_output_sr
-        for w, y in zip(waves, ys):
-            n = int(np.ceil(len(w) * ratio))  # librosa.resample: fix_length to ceil(L*ratio)
-            out.append(y[:n] if len(y) >= n else np.pad(y, (0, n - len(y))))
+        for dt in (np.float32, np.float64):
+            idx = [i for i, w in enumerate(waves) if (np.asarray(w).dtype == np.float64) == (dt == np.float64)]
+            if not idx:
+                continue
+            if dt not in self._out_resampler:
+                self._out_resampler[dt] = PolyphaseResampler(self.evaluationset_sr, self.model_output_sr, dtype=dt)
+            ys = self._out_resampler[dt].resample([np.asarray(waves[i], dtype=dt) for i in idx])
+            for i, y in zip(idx, ys):
+                n = int(np.ceil(len(waves[i]) * ratio))  # librosa.resample: fix_length to ceil(L*ratio)
+                out[i] = y[:n] if len(y) >= n else np.pad(y, (0, n - len(y)))
         return out
 
     def evaluate_batch(self, files):

@@ -8,11 +8,15 @@ from .engine import StftMetrics
 EPS = 1e-12
 
 
-def _as_wave(x):
+def _as_wave(x, keep_float64=False):
+    """float32 waveform; a float64 ESTIMATE stays float64: the reference's IIR low-pass filters return float64
+    (scipy sosfiltfilt) and librosa / torch keep such an estimate in float64 end to end (dtype_r2c, type
+    promotion) -- the kernels reproduce that (include/ssr_b200.h, ssr_stft_metrics_batched_f64est).  Targets
+    come from librosa.load in the reference and are float32 there; any other dtype is cast to float32."""
     a = np.asarray(x)
+    if a.dtype == np.float64 and keep_float64:
+        return a
     if a.dtype != np.float32:
-        # The reference keeps float64 inputs in float64 end to end (librosa dtype_r2c); the GPU path
-        # is float32-in like every waveform ssr_eval itself produces (librosa.load -> float32).
         a = a.astype(np.float32)
     return a
 
@@ -56,7 +60,7 @@ class AudioMetrics:
             "Error: Shape mismatch between target and estimation %s and %s"
             % (str(target.shape), str(est.shape)))
         n = min(target.shape[0], est.shape[0])
-        return _as_wave(est[:n]), _as_wave(target[:n])
+        return _as_wave(est[:n], keep_float64=True), _as_wave(target[:n])
 
     def evaluation(self, est, target, file=None):
         """Metrics of one (est, target) pair -> {"lsd","log_sispec","sispec","ssim"} floats

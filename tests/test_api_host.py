@@ -28,7 +28,8 @@ def test_pair_checks():
     with pytest.raises(AssertionError):
         AudioMetrics._check_pair(a[:, None], a)
     e, t = AudioMetrics._check_pair(np.ones(950, np.float64), a)
-    assert len(e) == len(t) == 950 and e.dtype == np.float32
+    # a float64 estimate stays float64 (the reference scores it in float64), the target is float32
+    assert len(e) == len(t) == 950 and e.dtype == np.float64 and t.dtype == np.float32
 
 
 def test_lowpass_dispatch_errors_and_iir():
