@@ -27,6 +27,7 @@ struct ssr_lowpass_plan {
   const float* win;          // float32(hann_periodic[n])
   const float* win_over_n;   // float32(hann[n] / N)
   const float* win_sq;       // float32(hann[n]^2)
+  const float* ws_tab;       // [hop]: overlap-added window^2 of an interior sample m, index m % hop
   const uint16_t* ppos;      // padded slot of frequency k after the DIF passes
 };
 
@@ -41,6 +42,7 @@ struct LpDev {
   const float* win_over_n;
   const float* win_sq;
   const uint16_t* ppos;
+  const float* ws_tab;
 };
 
 __device__ __forceinline__ long long lp_reflect(long long i, long long L) {
@@ -349,14 +351,33 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
     __syncthreads();
   }
 
-  for (int i = tid; i < span; i += kV2Threads) {
-    const long long m = m0 + i;
-    long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
-    long long fb = min(T - 1, m / hop);
-    float ws = 0.f;
-    for (long long f = fa; f <= fb; ++f) ws += P.win_sq[m - f * hop];
-    ws = fmaxf(ws, 1e-11f);
-    y[off + (m - N / 2)] = acc[i] / ws;
+  // Division by the overlap-added window^2.  For an interior sample (every frame that can cover it exists) the
+  // sum depends only on m % hop and comes from a table the plan built with the same float32 additions in the
+  // same order; m / hop and m % hop are tracked with 32-bit counters (m0 = blockIdx.x * chunk_hops * hop + N/2),
+  // so the 64-bit divisions and the 4-5 step loop only run for the few samples at the ends of an utterance.
+  {
+    int t = N / 2 + tid;
+    int q = t / hop, r = t - q * hop;
+    const long long q0 = (long long)blockIdx.x * chunk_hops;
+    for (int i = tid; i < span; i += kV2Threads) {
+      const long long m = m0 + i;
+      float ws;
+      if (m >= N - hop && q0 + q <= T - 1) {
+        ws = __ldg(P.ws_tab + r);
+      } else {
+        long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
+        long long fb = min(T - 1, m / hop);
+        ws = 0.f;
+        for (long long f = fa; f <= fb; ++f) ws += P.win_sq[m - f * hop];
+      }
+      ws = fmaxf(ws, 1e-11f);
+      y[off + (m - N / 2)] = acc[i] / ws;
+      r += kV2Threads;
+      while (r >= hop) {
+        r -= hop;
+        ++q;
+      }
+    }
   }
 }
 
@@ -383,7 +404,7 @@ static int lp_chunk_hops(int hop) {
 template <int LOGM>
 static int launch_lp(const ssr_lowpass_plan* plan, const float* x, const long long* offs,
                      const int* cut, float* y, int n, long long max_len, cudaStream_t st) {
-  LpDev P{plan->n_fft, plan->hop, plan->tw, plan->win, plan->win_over_n, plan->win_sq, plan->ppos};
+  LpDev P{plan->n_fft, plan->hop, plan->tw, plan->win, plan->win_over_n, plan->win_sq, plan->ppos, plan->ws_tab};
   const int ch = lp_chunk_hops(plan->hop);
   size_t smem = sizeof(cf) * (size_t)padded_size(plan->n_fft) + sizeof(float) * (size_t)ch * plan->hop;
   auto kern = k_stft_hard_lowpass<LOGM>;
@@ -400,7 +421,7 @@ static int launch_lp(const ssr_lowpass_plan* plan, const float* x, const long lo
 
 static int launch_lp_2048(const ssr_lowpass_plan* plan, const float* x, const long long* offs,
                           const int* cut, float* y, int n, long long max_len, cudaStream_t st) {
-  LpDev P{plan->n_fft, plan->hop, plan->tw, plan->win, plan->win_over_n, plan->win_sq, plan->ppos};
+  LpDev P{plan->n_fft, plan->hop, plan->tw, plan->win, plan->win_over_n, plan->win_sq, plan->ppos, plan->ws_tab};
   const int ch = lp_chunk_hops(plan->hop);
   size_t smem = sizeof(cf) * (size_t)(2048 + 128) + sizeof(float) * (size_t)ch * plan->hop;
   SSR_CUDA_TRY(cudaFuncSetAttribute(k_stft_hard_lowpass_2048, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -442,6 +463,8 @@ int ssr_lowpass_plan_create(ssr_lowpass_plan** out, int n_fft, int hop) {
   o = align_up(o + sizeof(float) * (size_t)N, 256);
   size_t o_pos = o;
   o = align_up(o + sizeof(uint16_t) * (size_t)N, 256);
+  size_t o_ws = o;
+  o = align_up(o + sizeof(float) * (size_t)hop, 256);
   std::vector<unsigned char> host(o, 0);
   cf* tw = reinterpret_cast<cf*>(host.data() + o_tw);
   float* w = reinterpret_cast<float*>(host.data() + o_w);
@@ -456,6 +479,14 @@ int ssr_lowpass_plan_create(ssr_lowpass_plan** out, int n_fft, int hop) {
     wn[n] = (float)(h / (double)N);
     w2[n] = (float)(h * h);
     ppos[n] = (uint16_t)pad_idx(dif_position(n, logM));
+  }
+  // interior overlap-added window^2: frames in ascending order = window offsets r + j*hop in DESCENDING j,
+  // float32 additions exactly as the kernels' edge loop performs them
+  float* ws_tab = reinterpret_cast<float*>(host.data() + o_ws);
+  for (int r = 0; r < hop; ++r) {
+    volatile float ws = 0.f;
+    for (int j = (N - 1 - r) / hop; j >= 0; --j) ws = ws + w2[r + j * hop];
+    ws_tab[r] = ws;
   }
   ssr_lowpass_plan* p = new ssr_lowpass_plan();
   p->n_fft = N;
@@ -476,6 +507,7 @@ int ssr_lowpass_plan_create(ssr_lowpass_plan** out, int n_fft, int hop) {
   p->win_over_n = reinterpret_cast<const float*>(d + o_wn);
   p->win_sq = reinterpret_cast<const float*>(d + o_w2);
   p->ppos = reinterpret_cast<const uint16_t*>(d + o_pos);
+  p->ws_tab = reinterpret_cast<const float*>(d + o_ws);
   *out = p;
   return SSR_OK;
 }
