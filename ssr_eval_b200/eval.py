@@ -14,7 +14,7 @@ import numpy as np
 from . import _native as N
 from .audio_io import load_audio, write_wav
 from .engine import PolyphaseResampler
-from .lowpass import lowpass, stft_hard_lowpass_batch
+from .lowpass import lowpass_batch, stft_hard_lowpass_batch
 from .metrics import AudioMetrics
 from .utils import dict_mean, write_json
 
@@ -111,16 +111,18 @@ class SSR_Eval_Helper:
                         if low_rate == sr:
                             low_rate -= 1
                         key = "proc_%s_%s_%s_%s" % (tag, low_rate, order, sr)
-                        for x, o in zip(xs, outs):
-                            o[key] = lowpass(x, low_rate // 2, sr, order=order, _type=ftype)
+                        ys = lowpass_batch(xs, low_rate // 2, sr, order=order, _type=ftype)  # one K7 launch
+                        for x, o, y in zip(xs, outs, ys):
+                            o[key] = y
                             assert o[key].shape == x.shape, str((o[key].shape, x.shape))
         if self.setting_subsampling is not None:
             for low_rate in self.setting_subsampling["cutoff_freq"]:
                 if low_rate == sr:
                     low_rate -= 1
                 key = "proc_subsampling_%s_%s" % (low_rate, sr)
-                for x, o in zip(xs, outs):
-                    o[key] = lowpass(x, low_rate // 2, sr, order=1, _type="subsampling")
+                ys = lowpass_batch(xs, low_rate // 2, sr, order=1, _type="subsampling")  # two K3 launches
+                for o, y in zip(outs, ys):
+                    o[key] = y
         if self.setting_mp3_compression is not None:
             raise NotImplementedError("mp3 degradation needs the external sox binary (eval.py:302-325); out of scope")
         if self.setting_fft is not None:

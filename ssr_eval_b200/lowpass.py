@@ -47,16 +47,19 @@ def align_length(x, y):
     return y[:Lx]
 
 
+def subsampling_batch(waves, lowpass_ratio, fs_ori=44100):
+    """``subsampling`` for a list of utterances: two K3 launches for the whole list."""
+    fs_down = int(lowpass_ratio * fs_ori)
+    xs = [np.asarray(w, dtype=np.float32) for w in waves]
+    ys = _resampler(fs_down, fs_ori).resample(xs)
+    ys = _resampler(fs_ori, fs_down).resample(ys)
+    return [y if len(y) == len(x) else align_length(x, y) for x, y in zip(xs, ys)]
+
+
 def subsampling(data, lowpass_ratio, fs_ori=44100):
     """Down- then up-sample by polyphase filtering (ssr_eval/lowpass.py:134-144; fs_ori stays
     44100 whatever the true rate is, as in the reference)."""
-    fs_down = int(lowpass_ratio * fs_ori)
-    x = np.asarray(data, dtype=np.float32)
-    y = _resampler(fs_down, fs_ori).resample([x])[0]
-    y = _resampler(fs_ori, fs_down).resample([y])[0]
-    if len(y) != len(data):
-        y = align_length(data, y)
-    return y
+    return subsampling_batch([data], lowpass_ratio, fs_ori)[0]
 
 
 def _design(order, band, btype, ftype):
@@ -78,11 +81,31 @@ def sosfiltfilt(sos, x):
     return sosfiltfilt_batch(sos, [np.asarray(x, dtype=np.float32)])[0]
 
 
+def lowpass_filter_batch(waves, highcut, fs, order, ftype):
+    """``lowpass_filter`` for a list of utterances: one K7 launch for the whole list."""
+    sos = _design(order, highcut / (0.5 * fs), "low", ftype)
+    ys = sosfiltfilt_batch(sos, [np.asarray(w, dtype=np.float32) for w in waves])
+    return [align_length(x, y) if len(y) != len(x) else y for x, y in zip(waves, ys)]
+
+
 def lowpass_filter(x, highcut, fs, order, ftype):
     """Zero-phase IIR low-pass (ssr_eval/lowpass.py:94-131): scipy design + GPU sosfiltfilt."""
-    sos = _design(order, highcut / (0.5 * fs), "low", ftype)
-    y = sosfiltfilt(sos, x)
-    return align_length(x, y) if len(y) != len(x) else y
+    return lowpass_filter_batch([x], highcut, fs, order, ftype)[0]
+
+
+def lowpass_batch(waves, highcut, fs, order=5, _type="butter"):
+    """``lowpass`` (same dispatch, same checks) for a list of utterances that share the filter settings."""
+    order = limit(order, high=10, low=2)
+    for data in waves:
+        _check_1d(data)
+    for name in ("butter", "cheby1", "ellip", "bessel"):
+        if _type in name:
+            return lowpass_filter_batch(waves, int(highcut), fs, order, name)
+    if _type in "subsampling":
+        return subsampling_batch(waves, lowpass_ratio=highcut / int(fs / 2))
+    if _type in "stft_hard":
+        return stft_hard_lowpass_batch(waves, [highcut / int(fs / 2)] * len(waves))
+    raise ValueError("Error: Unexpected filter type " + _type)
 
 
 def bandpass_filter(x, lowcut, highcut, fs, order, ftype):

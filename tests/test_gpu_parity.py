@@ -533,3 +533,39 @@ def test_resample_poly_float64_vs_scipy(up, down):
         want = resample_poly(w, up, down)
         assert y.dtype == np.float64 and y.shape == want.shape
         assert np.array_equal(y, want), (up, down, len(w), np.abs(y - want).max())
+
+
+def test_fuzz_stft_sizes_and_ragged_batches_vs_oracle():
+    """Seeded fuzz: random n_fft (powers of two, PFA sizes R*P, primes -> generic Bluestein), random hops, ragged
+    batches mixing hard-low-passed / noisy / scaled / float64 estimates; every pair against the oracle."""
+    from ssr_eval_b200.engine import StftMetrics
+    rng = np.random.default_rng(20260117)
+    sizes = [256, 512, 1024, 2048, 4096, 2229, 1114, 743, 1486, 557, 1031, 2053, 300, 1000, 3000]
+    for case in range(14):
+        n_fft = int(sizes[rng.integers(len(sizes))])
+        hop = int(rng.integers(max(1, n_fft // 8), n_fft // 2 + 1))
+        n = int(rng.integers(1, 6))
+        lens = [int(rng.integers(n_fft // 2 + 1, 9 * n_fft)) for _ in range(n)]
+        est, tgt = [], []
+        for i, L in enumerate(lens):
+            t = speech_like(L, sr=48000, seed=int(rng.integers(1 << 30)))
+            kind = int(rng.integers(4))
+            if kind == 0 and L > 1024:
+                e = oracle.lowpass(t, int(rng.integers(2000, 20000)), 48000, order=1, _type="stft_hard").astype(np.float32)
+            elif kind == 1 and L > 60:
+                e = oracle.lowpass(t, int(rng.integers(2000, 20000)), 48000, order=int(rng.integers(2, 9)), _type="butter")
+            elif kind == 2:
+                e = (float(rng.uniform(0.1, 2.0)) * t).astype(np.float32)
+            else:
+                e = (t + 10.0 ** rng.uniform(-5, -1) * rng.standard_normal(L)).astype(np.float32)
+            est.append(e)
+            tgt.append(t)
+        got = StftMetrics(n_fft, hop).metrics(est, tgt)
+        for i, L in enumerate(lens):
+            frames = 1 + L // hop
+            which = METRICS if (frames >= 7 and n_fft // 2 + 1 >= 7) else METRICS[:3]
+            want = oracle.evaluation(est[i], tgt[i], n_fft=n_fft, hop=hop, which=which)
+            tol = dict(TOL)
+            if want["sispec"] > 60:  # (near-)identical pair: the reference's own float32 cancellation noise
+                tol.pop("sispec")
+            _assert_metrics(dict(zip(METRICS, got[i])), want, f"case {case} n_fft {n_fft} hop {hop} L {L} {est[i].dtype}", tol)
