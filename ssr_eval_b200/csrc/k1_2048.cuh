@@ -35,7 +35,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
                     const long long* __restrict__ offsets, const int* __restrict__ item_start,
                     const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
                     double* __restrict__ partials, float* __restrict__ spec_e,
-                    float* __restrict__ spec_t, const long long* __restrict__ spec_off) {
+                    float* __restrict__ spec_t, const long long* __restrict__ spec_off, int* __restrict__ next_item) {
   constexpr int N = 2048, F = 1025, NW = kV2Threads / 32;
   constexpr int kTmemCols = RING ? 128 : 64;  // [0, 60) twiddles, [64, 128) sample ring
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -87,7 +87,8 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
   const cd* const t2 = tw2 + j2;
   __syncthreads();
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  __shared__ int item_slot;
+  for (int item = next_work_item(next_item, &item_slot); item < n_items; item = next_work_item(next_item, &item_slot)) {
     const int p = item_pair[item];
     const int c = item - item_start[p];
     const long long off = offsets[p];

@@ -123,8 +123,21 @@ __global__ void k_setup(const long long* __restrict__ offsets, int n, int n_fft,
   }
   if (hi == n) {
     item_start[n] = (int)it;
+    item_start[n + 1] = 0;  // work-item counter of the persistent kernels (dynamic scheduling)
     spec_off[n] = fr * F;
   }
+}
+
+// Persistent CTAs draw their work items from a counter instead of striding by gridDim.x: items differ in
+// length (the last chunk of a pair is short) and a static stride resonates with the items-per-pair period
+// (592 CTAs, 8 items per 5 s pair: every 8th CTA would only ever see the short items).  Which CTA computes an
+// item does not change its partial sums, so results stay bit-identical.
+__device__ __forceinline__ int next_work_item(int* counter, int* slot_smem) {
+  if (threadIdx.x == 0) *slot_smem = atomicAdd(counter, 1);
+  __syncthreads();
+  const int item = *slot_smem;
+  __syncthreads();  // the slot may be rewritten by the next call
+  return item;
 }
 
 

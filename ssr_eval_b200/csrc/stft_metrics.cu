@@ -91,8 +91,8 @@ static int plan_layout(const ssr_stft_plan* plan, const int64_t* offs, int n, un
     total_frames += T;
     if (T > max_T) max_T = T;
   }
-  // aim for ~8 work items per resident CTA slot (148 SMs x 2), bounded to [4, kMaxChunk] frames
-  long long want = 148LL * 3 * 8;
+  // ~32 work items per resident CTA slot (148 SMs x 4): with dynamic scheduling the tail is at most one item
+  long long want = 148LL * 4 * 32;
   long long chunk = (total_frames + want - 1) / want;
   if (chunk < 4) chunk = 4;
   if (chunk > kMaxChunk) chunk = kMaxChunk;
@@ -112,7 +112,7 @@ static int plan_layout(const ssr_stft_plan* plan, const int64_t* offs, int n, un
   w->tiles_per_pair = w->tiles_x * tiles_y;
   size_t o = 0;
   w->item_start = o;
-  o = align_up(o + sizeof(int) * (size_t)(n + 1), 256);
+  o = align_up(o + sizeof(int) * (size_t)(n + 2), 256);  // + the work-item counter
   w->item_pair = o;
   o = align_up(o + sizeof(int) * (size_t)n_items, 256);
   w->spec_off = o;
@@ -234,7 +234,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     auto kern = k_stft_metrics_pfa<NQ_, FX>;                                                         \
     SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
     kern<<<gp, kV2Threads, smem_p, st>>>(plan->pdev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
-                                         w.chunk, flags, partials, spec_e, spec_t, spec_off);        \
+                                         w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1); \
   } while (0)
     if (nq <= 6) {
       if (lsd_only) SSR_PFA_LAUNCH(6, 1);
@@ -276,7 +276,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     auto kern = ring ? k_stft_metrics_2048<FX, true> : k_stft_metrics_2048<FX, false>;              \
     SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
     kern<<<g2, kV2Threads, smem2, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, w.n_items, \
-                                        w.chunk, flags, partials, spec_e, spec_t, spec_off);        \
+                                        w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1); \
   } while (0)
     if (fixed == 1) SSR_V2_LAUNCH(1);
     else if (fixed == 7) SSR_V2_LAUNCH(7);
