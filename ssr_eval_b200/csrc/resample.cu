@@ -60,7 +60,9 @@ k_resample(const T* __restrict__ x, const long long* __restrict__ in_off, T* __r
 // only x is loaded in the inner loop (through L1: consecutive lanes read consecutive-ish samples).
 // The float32 multiply / add order per output is unchanged (ascending input index), so results stay
 // bit-identical to scipy.
-template <int KMAX, int R>
+// EXACT: K == KMAX (the common ratios get their own instantiation, so the unrolled tap loops carry no run-time
+// `k < K` predicates and no dead iterations)
+template <int KMAX, int R, bool EXACT>
 __global__ void __launch_bounds__(512)
 k_resample_tiled(const float* __restrict__ x, const long long* __restrict__ in_off, float* __restrict__ y,
                  const long long* __restrict__ out_off, int u0, int up, int down, int n_pre_pad,
@@ -82,7 +84,7 @@ k_resample_tiled(const float* __restrict__ x, const long long* __restrict__ in_o
   }
   float h[KMAX];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) h[k] = (k < K) ? __ldg(bank + phase * K + k) : 0.f;
+  for (int k = 0; k < KMAX; ++k) h[k] = (EXACT || k < K) ? __ldg(bank + phase * K + k) : 0.f;
   const long long step = (long long)(TP / up) * down;  // input advance per TP outputs (TP % up == 0)
   // G outputs are accumulated together: G independent float32 add chains and G*K loads in flight
   constexpr int G = 4;
@@ -103,7 +105,7 @@ k_resample_tiled(const float* __restrict__ x, const long long* __restrict__ in_o
     if (inner[0] && inner[1] && inner[2] && inner[3]) {  // interior: no bounds checks
 #pragma unroll
       for (int k = KMAX - 1; k >= 0; --k)
-        if (k < K) {
+        if (EXACT || k < K) {
 #pragma unroll
           for (int g = 0; g < G; ++g) acc[g] = __fadd_rn(acc[g], __fmul_rn(__ldg(px[g] - k), h[k]));
         }
@@ -115,7 +117,7 @@ k_resample_tiled(const float* __restrict__ x, const long long* __restrict__ in_o
 #pragma unroll
         for (int k = KMAX - 1; k >= 0; --k) {
           const long long ii = ih - k;
-          if (k < K && ii >= 0 && ii < n_in) acc[g] = __fadd_rn(acc[g], __fmul_rn(__ldg(xu + ii), h[k]));
+          if ((EXACT || k < K) && ii >= 0 && ii < n_in) acc[g] = __fadd_rn(acc[g], __fmul_rn(__ldg(xu + ii), h[k]));
         }
       }
     }
@@ -248,12 +250,17 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
       dim3 grid((unsigned)((max_out + (long long)TP * R - 1) / ((long long)TP * R)), nu);
       const long long* io = reinterpret_cast<const long long*>(in_offsets_dev);
       const long long* oo = reinterpret_cast<const long long*>(out_offsets_dev);
-      if (plan->K <= 24)
-        k_resample_tiled<24, R><<<grid, TP, 0, st>>>(x_dev, io, y_dev, oo, u0, plan->up, plan->down,
-                                                     plan->n_pre_pad, plan->n_pre_remove, plan->K, static_cast<const float*>(plan->bank));
-      else
-        k_resample_tiled<48, R><<<grid, TP, 0, st>>>(x_dev, io, y_dev, oo, u0, plan->up, plan->down,
-                                                     plan->n_pre_pad, plan->n_pre_remove, plan->K, static_cast<const float*>(plan->bank));
+#define SSR_K3_LAUNCH(KM, EX)                                                                              \
+  k_resample_tiled<KM, R, EX><<<grid, TP, 0, st>>>(x_dev, io, y_dev, oo, u0, plan->up, plan->down,        \
+                                                   plan->n_pre_pad, plan->n_pre_remove, plan->K,          \
+                                                   static_cast<const float*>(plan->bank))
+      if (plan->K == 21) SSR_K3_LAUNCH(21, true);       // 44.1k <-> 48k up (160/147), 16k -> 44.1k (441/160)
+      else if (plan->K == 22) SSR_K3_LAUNCH(22, true);  // 48k -> 44.1k (147/160)
+      else if (plan->K <= 24) SSR_K3_LAUNCH(24, false);
+      else if (plan->K <= 32) SSR_K3_LAUNCH(32, false);
+      else if (plan->K <= 40) SSR_K3_LAUNCH(40, false);
+      else SSR_K3_LAUNCH(48, false);
+#undef SSR_K3_LAUNCH
       SSR_LAUNCH_CHECK("k_resample_tiled");
     }
     return SSR_OK;
