@@ -27,6 +27,7 @@ struct ssr_splice_plan {
   const double* win_half;    // 0.5 * hann[n]
   const double* win_over_n;  // hann[n] / n_fft
   const double* win_sq;      // hann[n]^2
+  const float* ws_tab;       // [hop]: window_sumsquare of an interior sample m, index m % hop
 };
 
 namespace ssr {
@@ -37,6 +38,7 @@ struct SpDev {
   const double* win_half;
   const double* win_over_n;
   const double* win_sq;
+  const float* ws_tab;
 };
 
 __device__ __forceinline__ long long sp_reflect(long long i, long long L) {
@@ -230,15 +232,34 @@ k_stft_splice_istft_2048(SpDev P, const float* __restrict__ xin, const float* __
     __syncthreads();
   }
 
-  for (int i = tid; i < span; i += kV2Threads) {
-    const long long m = m0 + i;
-    long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
-    long long fb = min(T - 1, m / hop);
-    float ws = 0.f;  // librosa.filters.window_sumsquare: float32 buffer += float64 hann^2, frame by frame
-    for (long long f = fa; f <= fb; ++f) ws = (float)((double)ws + __ldg(P.win_sq + (m - f * hop)));
-    float val = acc[i];
-    if (ws > 1.17549435e-38f) val = val / ws;
-    y[off + (m - N / 2)] = val;
+  // librosa.filters.window_sumsquare: float32 buffer += float64 hann^2, frame by frame.  Interior samples (every
+  // frame that can cover them exists) take the sum from a plan table built with the same additions in the same
+  // order, indexed by m % hop through 32-bit counters (m0 = blockIdx.x * chunk_hops * hop + N/2); only the ends
+  // of an utterance run the 64-bit divisions and the loop.
+  {
+    int t = N / 2 + tid;
+    int q = t / hop, r = t - q * hop;
+    const long long q0 = (long long)blockIdx.x * chunk_hops;
+    for (int i = tid; i < span; i += kV2Threads) {
+      const long long m = m0 + i;
+      float ws;
+      if (m >= N - hop && q0 + q <= T - 1) {
+        ws = __ldg(P.ws_tab + r);
+      } else {
+        long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
+        long long fb = min(T - 1, m / hop);
+        ws = 0.f;
+        for (long long f = fa; f <= fb; ++f) ws = (float)((double)ws + __ldg(P.win_sq + (m - f * hop)));
+      }
+      float val = acc[i];
+      if (ws > 1.17549435e-38f) val = val / ws;
+      y[off + (m - N / 2)] = val;
+      r += kV2Threads;
+      while (r >= hop) {
+        r -= hop;
+        ++q;
+      }
+    }
   }
 }
 
@@ -263,6 +284,8 @@ int ssr_splice_plan_create(ssr_splice_plan** out, int n_fft, int hop) {
   o = align_up(o + sizeof(double) * (size_t)N, 256);
   size_t o_w2 = o;
   o = align_up(o + sizeof(double) * (size_t)N, 256);
+  size_t o_ws = o;
+  o = align_up(o + sizeof(float) * (size_t)hop, 256);
   std::vector<unsigned char> host(o, 0);
   cd* tw = reinterpret_cast<cd*>(host.data() + o_tw);
   double* wh = reinterpret_cast<double*>(host.data() + o_wh);
@@ -275,6 +298,12 @@ int ssr_splice_plan_create(ssr_splice_plan** out, int n_fft, int hop) {
     wh[n] = 0.5 * h;
     wn[n] = h / (double)N;
     w2[n] = h * h;
+  }
+  float* ws_tab = reinterpret_cast<float*>(host.data() + o_ws);
+  for (int r = 0; r < hop; ++r) {  // frames ascending = window offsets r + j*hop descending
+    volatile float ws = 0.f;
+    for (int j = (N - 1 - r) / hop; j >= 0; --j) ws = (float)((double)ws + w2[r + j * hop]);
+    ws_tab[r] = ws;
   }
   ssr_splice_plan* p = new ssr_splice_plan();
   p->n_fft = N;
@@ -293,6 +322,7 @@ int ssr_splice_plan_create(ssr_splice_plan** out, int n_fft, int hop) {
   p->win_half = reinterpret_cast<const double*>(d + o_wh);
   p->win_over_n = reinterpret_cast<const double*>(d + o_wn);
   p->win_sq = reinterpret_cast<const double*>(d + o_w2);
+  p->ws_tab = reinterpret_cast<const float*>(d + o_ws);
   *out = p;
   return SSR_OK;
 }
@@ -318,7 +348,7 @@ int ssr_stft_splice_istft_batched(const ssr_splice_plan* plan, const float* x_de
   int ch = 16384 / plan->hop;  // accumulator <= 64 KB
   if (ch > 32) ch = 32;
   if (ch < 1) ch = 1;
-  SpDev P{plan->hop, plan->tw, plan->win_half, plan->win_over_n, plan->win_sq};
+  SpDev P{plan->hop, plan->tw, plan->win_half, plan->win_over_n, plan->win_sq, plan->ws_tab};
   size_t smem = sizeof(cd) * (size_t)(2048 + 256) + sizeof(float) * (size_t)ch * plan->hop;
   SSR_CUDA_TRY(cudaFuncSetAttribute(k_stft_splice_istft_2048, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));

@@ -41,7 +41,7 @@ def report(name, ms, units, unit_name, alg_bytes):
 
 
 def main():
-    which = set(sys.argv[1:]) or {"k1", "k1blue", "k3", "k4", "k7"}
+    which = set(sys.argv[1:]) or {"k1", "k1blue", "k3", "k4", "k6", "k7"}
     g = torch.Generator(device=dev)
     g.manual_seed(0)
     if "k1" in which:
@@ -91,6 +91,27 @@ def main():
         report("K4 stft_hard 2048/441 (5 s @ 44.1k)", ms, n, "utterances", 8 * n * L)
 
 
+    if "k6" in which:
+        import ctypes
+        from ssr_eval_b200.engine import SpliceIstft
+        n, L = 1024, 220500
+        x = 0.1 * torch.randn(n * L, generator=g, device=dev)
+        o = x + 0.01 * torch.randn(n * L, generator=g, device=dev)
+        sp = SpliceIstft(2048, 512)
+        off = offsets_of([L] * n)
+        off_d = torch.from_numpy(off).to(dev)
+        cb = torch.full((n,), 372, dtype=torch.int32, device=dev)
+        y = torch.empty_like(o)
+        vp = ctypes.c_void_p
+
+        def run6():
+            N.check(N.lib().ssr_stft_splice_istft_batched(sp._plan, vp(x.data_ptr()), vp(o.data_ptr()), vp(off.ctypes.data),
+                                                          vp(off_d.data_ptr()), n, vp(cb.data_ptr()), vp(y.data_ptr()),
+                                                          vp(torch.cuda.current_stream().cuda_stream)),
+                    "ssr_stft_splice_istft_batched")
+        ms = timeit(run6, iters=3, warm=1)
+        report("K6 postprocessing splice + ISTFT 2048/512 (5 s @ 44.1k)", ms, n, "utterances", 12 * n * L)
+        del x, o, y
     if "k7" in which:
         from scipy.signal import butter, sosfilt_zi
         import ctypes
