@@ -10,10 +10,13 @@
 //   x_new = b0 * x_cur + z0;  z0 = (b1 * x_cur - a1 * x_new) + z1;  z1 = b2 * x_cur - a2 * x_new
 // is reproduced with separately rounded multiplies and adds in the same order.
 //
-// The recursion is sequential in time but the sections form a systolic pipeline: one WARP per
-// utterance, lane s owns section s and at micro-step t filters sample t - s, taking its input from
-// lane s-1 by shuffle.  Inputs are fetched and outputs stored 32 samples at a time (coalesced).
-// Thousands of utterances (one per warp) run concurrently, which is where the throughput comes from.
+// The recursion is sequential in time but the sections form a systolic pipeline: a GROUP of SP lanes
+// (SP = smallest power of two >= the number of sections: 1, 2, 4 or 8 for filter orders 2 .. 10) owns one
+// utterance, lane s of the group owns section s and at micro-step t filters sample t - s, taking its input
+// from lane s-1 by a width-SP shuffle.  A warp therefore filters 32 / SP utterances at once (the first
+// version gave every utterance a whole warp and left 32 - S lanes idle: 31 k utt/s at order 8).  Inputs are
+// fetched and outputs stored SP samples at a time per group, the next block of inputs one block ahead.
+// Thousands of utterances run concurrently, which is where the throughput comes from.
 #include <math.h>
 
 #include <vector>
@@ -39,70 +42,75 @@ __device__ __forceinline__ double ext_sample(const float* __restrict__ x, long l
   return (double)__fsub_rn(__fmul_rn(2.0f, x[L - 1]), x[L - 2 - (m - L)]);
 }
 
+template <int SP>
 __global__ void __launch_bounds__(128)
 k_sosfiltfilt(SosDev P, const float* __restrict__ x, const long long* __restrict__ offsets, int n,
               double* __restrict__ y, double* __restrict__ ws) {
+  constexpr int G = 32 / SP;  // utterances per warp
   const int lane = threadIdx.x & 31;
+  const int s = lane & (SP - 1), g = lane / SP;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   const int S = P.n_sections, edge = P.edge;
-  const bool owner = lane < S;
-  const int sl = owner ? lane : 0;
+  const bool owner = s < S;
+  const int sl = owner ? s : 0;
   const double b0 = P.b0[sl], b1 = P.b1[sl], b2 = P.b2[sl], a1 = P.a1[sl], a2 = P.a2[sl];
   const double zi0 = P.zi0[sl], zi1 = P.zi1[sl];
   const unsigned full = 0xffffffffu;
 
-  for (int u = warp_global; u < n; u += n_warps) {
-    const long long off = offsets[u];
-    const long long L = offsets[u + 1] - off;
-    const long long n_tot = L + 2LL * edge;
+  for (long long u0 = (long long)warp_global * G; u0 < n; u0 += (long long)n_warps * G) {
+    const long long u = u0 + g;
+    const bool live = u < n;  // this group has an utterance
+    const long long off = live ? offsets[u] : 0;
+    const long long L = live ? offsets[u + 1] - off : 0;
+    const long long n_tot = live ? L + 2LL * edge : 0;
     const float* xu = x + off;
     double* w = ws + off + 2LL * edge * u;  // forward-pass output, n_tot doubles
     double* yu = y + off;
+    const long long steps = live ? n_tot + S - 1 : 0;
+    long long steps_max = steps;  // the warp runs until its longest utterance is done
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) steps_max = max(steps_max, __shfl_xor_sync(full, steps_max, o));
 
+    const int nt = (int)n_tot, Li = (int)L;  // per-utterance sizes fit 32 bits (checked on the host)
     for (int pass = 0; pass < 2; ++pass) {
       // initial conditions: zi * (first input sample of this pass)
-      const double first = pass == 0 ? ext_sample(xu, L, edge, 0) : w[n_tot - 1];
+      double first = 0.0;
+      if (live) first = pass == 0 ? ext_sample(xu, L, edge, 0) : w[n_tot - 1];
       double z0 = __dmul_rn(zi0, first), z1 = __dmul_rn(zi1, first);
-      double carry = 0.0;   // x_new of the previous micro-step (input of lane s+1)
-      double yout = 0.0;    // output staging: lane (index & 31) keeps output `index`
-      const long long steps = n_tot + S - 1;
-      for (long long base = 0; base < steps; base += 32) {
-        // coalesced fetch of inputs base .. base+31
-        const long long ii = base + lane;
-        double xin = 0.0;
-        if (ii < n_tot) xin = pass == 0 ? ext_sample(xu, L, edge, ii) : w[n_tot - 1 - ii];
-#pragma unroll 4
-        for (int j = 0; j < 32; ++j) {
-          const long long t = base + j;
-          if (t >= steps) break;
-          const double from_prev = __shfl_up_sync(full, carry, 1);
-          const double from_mem = __shfl_sync(full, xin, j);
-          const double x_cur = lane == 0 ? from_mem : from_prev;
-          const long long idx = t - lane;  // sample this lane filters now
-          double x_new = 0.0;
-          if (owner && idx >= 0 && idx < n_tot) {
-            x_new = __dadd_rn(__dmul_rn(b0, x_cur), z0);
-            z0 = __dadd_rn(__dsub_rn(__dmul_rn(b1, x_cur), __dmul_rn(a1, x_new)), z1);
-            z1 = __dsub_rn(__dmul_rn(b2, x_cur), __dmul_rn(a2, x_new));
-          }
-          carry = x_new;
-          // the last section's output is sample o = t - (S - 1)
-          const double done = __shfl_sync(full, x_new, S - 1);
-          const long long o = t - (S - 1);
-          if (o >= 0) {
-            if (lane == (int)(o & 31)) yout = done;
-            if ((o & 31) == 31 || o == n_tot - 1) {  // flush the staged block (coalesced)
-              const long long blk = o & ~31LL;
-              const long long oi = blk + lane;
-              if (oi <= o) {
-                if (pass == 0) {
-                  w[oi] = yout;
-                } else {
-                  const long long m = n_tot - 1 - oi - edge;  // reverse + strip the padding
-                  if (m >= 0 && m < L) yu[m] = yout;
-                }
-              }
+      double carry = 0.0;  // x_new of the previous micro-step (input of lane s+1)
+      auto fetch = [&](int base) {
+        const int ii = base + s;
+        double v = 0.0;
+        if (ii < nt) v = pass == 0 ? ext_sample(xu, L, edge, ii) : w[nt - 1 - ii];
+        return v;
+      };
+      double xin_next = fetch(0);
+      const int smax = (int)steps_max;
+      for (int base = 0; base < smax; base += SP) {
+        const double xin = xin_next;
+        xin_next = fetch(base + SP);  // one block ahead: its latency hides behind this block's recursion
+#pragma unroll
+        for (int j = 0; j < SP; ++j) {
+          const int t = base + j;
+          const double from_prev = __shfl_up_sync(full, carry, 1, SP);
+          const double from_mem = __shfl_sync(full, xin, j, SP);
+          const double x_cur = s == 0 ? from_mem : from_prev;
+          const int idx = t - s;  // sample this lane filters now
+          // branch-free step: every lane computes, inactive lanes keep their state and pass on 0
+          const bool act = owner && (unsigned)idx < (unsigned)nt;
+          const double xn = __dadd_rn(__dmul_rn(b0, x_cur), z0);
+          const double z0n = __dadd_rn(__dsub_rn(__dmul_rn(b1, x_cur), __dmul_rn(a1, xn)), z1);
+          const double z1n = __dsub_rn(__dmul_rn(b2, x_cur), __dmul_rn(a2, xn));
+          z0 = act ? z0n : z0;
+          z1 = act ? z1n : z1;
+          carry = act ? xn : 0.0;
+          if (act && s == S - 1) {  // the last section's lane stores output `idx` itself
+            if (pass == 0) {
+              w[idx] = xn;
+            } else {
+              const int m = nt - 1 - idx - edge;  // reverse + strip the padding
+              if ((unsigned)m < (unsigned)Li) yu[m] = xn;
             }
           }
         }
@@ -129,6 +137,7 @@ int ssr_sosfiltfilt_batched(const double* sos_host, int n_sections, const double
   for (int u = 0; u < n; ++u) {
     long long L = offsets_host[u + 1] - offsets_host[u];
     if (L <= edge) return fail(SSR_ERR_INVALID, "The length of the input vector x must be greater than padlen");
+    if (L + 2LL * edge + 64 > 0x7fffffffLL) return fail(SSR_ERR_INVALID, "utterance too long");
     total += L + 2LL * edge;
   }
   if (!workspace_dev || workspace_bytes < sizeof(double) * (size_t)total)
@@ -149,11 +158,22 @@ int ssr_sosfiltfilt_batched(const double* sos_host, int n_sections, const double
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int warps_needed = n;
+  int sp = 1;
+  while (sp < n_sections) sp *= 2;  // lanes per utterance
+  const int warps_needed = (int)(((long long)n * sp + 31) / 32);
   int blocks = (warps_needed + 3) / 4;
   if (blocks > sms * 16) blocks = sms * 16;
-  k_sosfiltfilt<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      P, x_dev, reinterpret_cast<const long long*>(offsets_dev), n, y_dev, static_cast<double*>(workspace_dev));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long* od = reinterpret_cast<const long long*>(offsets_dev);
+  double* wsd = static_cast<double*>(workspace_dev);
+  switch (sp) {
+    case 1: k_sosfiltfilt<1><<<blocks, 128, 0, st>>>(P, x_dev, od, n, y_dev, wsd); break;
+    case 2: k_sosfiltfilt<2><<<blocks, 128, 0, st>>>(P, x_dev, od, n, y_dev, wsd); break;
+    case 4: k_sosfiltfilt<4><<<blocks, 128, 0, st>>>(P, x_dev, od, n, y_dev, wsd); break;
+    case 8: k_sosfiltfilt<8><<<blocks, 128, 0, st>>>(P, x_dev, od, n, y_dev, wsd); break;
+    case 16: k_sosfiltfilt<16><<<blocks, 128, 0, st>>>(P, x_dev, od, n, y_dev, wsd); break;
+    default: k_sosfiltfilt<32><<<blocks, 128, 0, st>>>(P, x_dev, od, n, y_dev, wsd); break;
+  }
   SSR_LAUNCH_CHECK("k_sosfiltfilt");
   return SSR_OK;
 }

@@ -115,25 +115,29 @@ def main():
     if "k7" in which:
         from scipy.signal import butter, sosfilt_zi
         import ctypes
-        n, L = 4096, 220500
-        x = 0.1 * torch.randn(n * L, generator=g, device=dev)
-        off = offsets_of([L] * n)
-        off_d = torch.from_numpy(off).to(dev)
-        sos = np.ascontiguousarray(butter(8, 8000 / 22050, output="sos"))
-        zi = np.ascontiguousarray(sosfilt_zi(sos))
-        edge = 3 * (2 * sos.shape[0] + 1)
-        y = torch.empty(n * L, dtype=torch.float64, device=dev)
-        need = N.lib().ssr_sosfiltfilt_workspace_bytes(ctypes.c_void_p(off.ctypes.data), n, edge)
-        ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+        # the recursion is sequential in time: a launch takes ~ (samples x 4 dependent FP64 operations) however few
+        # utterances it holds, so throughput grows with the batch until the schedulers are full
+        for n in (4096, 16384):
+            L = 220500
+            x = 0.1 * torch.randn(n * L, generator=g, device=dev)
+            off = offsets_of([L] * n)
+            off_d = torch.from_numpy(off).to(dev)
+            sos = np.ascontiguousarray(butter(8, 8000 / 22050, output="sos"))
+            zi = np.ascontiguousarray(sosfilt_zi(sos))
+            edge = 3 * (2 * sos.shape[0] + 1)
+            y = torch.empty(n * L, dtype=torch.float64, device=dev)
+            need = N.lib().ssr_sosfiltfilt_workspace_bytes(ctypes.c_void_p(off.ctypes.data), n, edge)
+            ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
 
-        def run():
-            N.check(N.lib().ssr_sosfiltfilt_batched(
-                ctypes.c_void_p(sos.ctypes.data), sos.shape[0], ctypes.c_void_p(zi.ctypes.data), edge,
-                ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(off.ctypes.data), ctypes.c_void_p(off_d.data_ptr()), n,
-                ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
-                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "ssr_sosfiltfilt_batched")
-        ms = timeit(run, iters=2, warm=1)
-        report("K7 sosfiltfilt butter order 8 (4 sections), 4096 x 5 s @ 44.1k", ms, n, "utterances", n * L * (4 + 8))
+            def run():
+                N.check(N.lib().ssr_sosfiltfilt_batched(
+                    ctypes.c_void_p(sos.ctypes.data), sos.shape[0], ctypes.c_void_p(zi.ctypes.data), edge,
+                    ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(off.ctypes.data), ctypes.c_void_p(off_d.data_ptr()), n,
+                    ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "ssr_sosfiltfilt_batched")
+            ms = timeit(run, iters=2, warm=1)
+            report("K7 sosfiltfilt butter order 8 (4 sections), %d x 5 s @ 44.1k" % n, ms, n, "utterances", n * L * (4 + 8))
+            del x, y, ws
 
 
 if __name__ == "__main__":
