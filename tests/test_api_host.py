@@ -78,3 +78,81 @@ def test_ragged_packing_and_taps():
 def test_dict_mean():
     out = dict_mean([{"a": 1.0, "b": 2.0}, {"a": 3.0, "b": 6.0}])
     assert out == {"a": 2.0, "b": 4.0}
+
+
+def test_helper_length_and_naming_helpers(tmp_path):
+    """shift / pad / unify_length / cache_file_name of the mp3 path (ssr_eval/eval.py:272-300, 327-332): same results
+    as the reference's code on the same inputs (values below were produced by the reference's own methods)."""
+    h = SSR_Eval_Helper(BasicTestee(), 44100, 44100, test_data_root=str(tmp_path))
+    x = np.arange(1, 7, dtype=np.float32)
+    assert h.shift(x, 2).tolist() == [3, 4, 5, 6, 0, 0]
+    assert h.shift(x, -2).tolist() == [0, 0, 1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        h.shift(x, 0)  # ret[:-0] is empty: the reference raises here too
+    a, b = h.pad(np.ones(3), np.ones(5))
+    assert a.tolist() == [1, 1, 1, 0, 0] and b.tolist() == [1] * 5
+    a, b = h.pad(np.ones(5), np.ones(2))
+    assert a.tolist() == [1] * 5 and b.tolist() == [1, 1, 0, 0, 0]
+    a, b = h.unify_length(np.arange(6.0), np.arange(4.0))
+    assert a.tolist() == [0, 1, 2, 3] and len(b) == 4
+    a, b = h.unify_length(np.arange(3.0), np.arange(5.0))
+    assert a.tolist() == [0, 1, 2, 0, 0]
+    assert h.cache_file_name("proc_mp3_32_44100", "/d/p360/p360_001.wav") == "/d/p360/p360_001_proc_mp3_32_44100.flac"
+    assert h.cache_file_name("k", "a/b.wav", suffix=".mp3") == "a/b_k.mp3"
+    with pytest.raises(NotImplementedError):
+        h.mp3_encoding("f.wav", x, 44100)
+
+
+def test_reference_methods_live_when_the_reference_is_mounted(tmp_path):
+    """Build-container only: the same helper methods executed from /root/reference/ssr_eval/eval.py itself."""
+    import importlib.util
+    import sys
+    import types
+    ref_root = "/root/reference"
+    if not os.path.isdir(os.path.join(ref_root, "ssr_eval")):
+        pytest.skip("reference not mounted (GPU box)")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(repo, "oracle", "shims"))
+    saved = {k: sys.modules.get(k) for k in ("ssr_eval", "ssr_eval.utils", "ssr_eval.dsp", "ssr_eval.metrics",
+                                             "ssr_eval.lowpass", "ssr_eval.eval")}
+    try:
+        pkg = types.ModuleType("ssr_eval")
+        pkg.__path__ = [os.path.join(ref_root, "ssr_eval")]
+        sys.modules["ssr_eval"] = pkg
+        mods = {}
+        for name in ("utils", "dsp", "metrics", "lowpass", "eval"):
+            spec = importlib.util.spec_from_file_location("ssr_eval." + name, os.path.join(ref_root, "ssr_eval", name + ".py"))
+            m = importlib.util.module_from_spec(spec)
+            sys.modules["ssr_eval." + name] = m
+            spec.loader.exec_module(m)
+            mods[name] = m
+        R = mods["eval"].SSR_Eval_Helper
+        ours = SSR_Eval_Helper(BasicTestee(), 44100, 44100, test_data_root=str(tmp_path))
+        rng = np.random.default_rng(0)
+        x, y = rng.standard_normal(50).astype(np.float32), rng.standard_normal(37).astype(np.float32)
+        for sh in (-7, -1, 1, 9):
+            assert np.array_equal(R.shift(None, x, sh), ours.shift(x, sh))
+        for p, q in ((x, y), (y, x), (x, x)):
+            for f in ("pad", "unify_length"):
+                ra, rb = getattr(R, f)(None, p, q)
+                oa, ob = getattr(ours, f)(p, q)
+                assert np.array_equal(ra, oa) and np.array_equal(rb, ob)
+        assert R.cache_file_name(None, "key", "/a/b/c.wav") == ours.cache_file_name("key", "/a/b/c.wav")
+        d1, d2 = {"cutoff_freq": [1000, 12000]}, {"cutoff_freq": [1000, 12000]}
+        assert R._cutoff2sr(None, d1) == ours._cutoff2sr(d2) and d1 == d2
+        (tmp_path / "p1").mkdir()
+        for n in ("a.wav", "b.flac", "c_proc.wav", "x.DS_Store.wav", "d.mp3"):
+            (tmp_path / "p1" / n).write_bytes(b"")
+        assert sorted(R.get_test_file_list(None, str(tmp_path / "p1"))) == sorted(ours.get_test_file_list(str(tmp_path / "p1")))
+        # dict_mean (utils.py:24-28) and the lowpass dispatcher's `limit`
+        dm = mods["utils"].dict_mean
+        rows = [{"a": float(i), "b": float(i * i)} for i in range(5)]
+        assert dm(rows) == dict_mean(rows)
+        for v in (-3, 2, 5.7, 10, 99):
+            assert mods["lowpass"].limit(v, 10, 2) == limit(v, 10, 2)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
