@@ -1,5 +1,6 @@
 // k2_ssim.cuh -- K2 (7x7 box-window SSIM, cp.async row pipeline) and the fixed-order finalize kernel.
 #pragma once
+#include "f32x2.cuh"
 #include "k1_common.cuh"
 
 namespace ssr {
@@ -8,11 +9,12 @@ namespace ssr {
 // K2: SSIM of two (T, F) float32 magnitude images, valid 7x7 windows only (skimage crops the
 // 3-pixel border, so the reflect boundary mode of uniform_filter never reaches the mean).
 // One CTA = one tile of kSsimTR x kSsimTC window positions, 128 threads, TWO adjacent columns per
-// thread.  Rows stream through a double-buffered shared row buffer; per row a thread forms the
-// horizontal 7-sums of (x, y, xx, yy, xy) for its two columns (sliding: the second column reuses the
-// first column's inner sum) and updates RUNNING vertical 7-sums: V += h_new - h_oldest, with the last
-// seven h kept in a register ring (unrolled-by-7 loop).  The running sums restart in every tile, so
-// the result does not depend on how the batch was partitioned.
+// thread.  Rows stream through a 4-stage shared row buffer that holds, per column, the PAIR (estimate, target);
+// per row a thread forms the horizontal 7-sums of (x, y), (xx, yy) and xy for its two columns (sliding: the
+// second column reuses the first column's inner sum) and updates RUNNING vertical 7-sums: V += h_new -
+// h_oldest, with the last seven h kept in a register ring (unrolled-by-7 loop).  Everything that exists for x
+// and for y is one packed FADD2 / FMUL2 / FFMA2 on the pair (f32x2.cuh): same roundings, half the issue slots.
+// The running sums restart in every tile, so the result does not depend on how the batch was partitioned.
 // ---------------------------------------------------------------------------------------------
 constexpr int kSsimThreads = 128;
 
@@ -39,20 +41,34 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   const float* E = spec_e + spec_off[p];
   const float* G = spec_t + spec_off[p];
   constexpr int RB = kSsimTC + 8, STAGES = 4;
-  __shared__ __align__(16) float rowbuf[STAGES][2][RB];
+  // row buffer: per column the pair (estimate, target) -- the pair is the unit every packed operation below works on
+  __shared__ __align__(16) float2 rowbuf[STAGES][RB];
   __shared__ double red[kSsimThreads / 32];
 
-  float ring[7][10];
+  // per output column o (2 per thread): vertical running sums V1 = (sum x, sum y), V2 = (sum xx, sum yy), Vxy and
+  // the ring of the last seven horizontal sums; all float2 arithmetic is FADD2 / FMUL2 / FFMA2 (f32x2.cuh)
+  float2 R1[7][2], R2[7][2];
+  float Rxy[7][2];
 #pragma unroll
   for (int s = 0; s < 7; ++s)
 #pragma unroll
-    for (int q = 0; q < 10; ++q) ring[s][q] = 0.f;
-  float V[10];
+    for (int o = 0; o < 2; ++o) {
+      R1[s][o] = make_float2(0.f, 0.f);
+      R2[s][o] = make_float2(0.f, 0.f);
+      Rxy[s][o] = 0.f;
+    }
+  float2 V1[2], V2[2];
+  float Vxy[2];
 #pragma unroll
-  for (int q = 0; q < 10; ++q) V[q] = 0.f;
+  for (int o = 0; o < 2; ++o) {
+    V1[o] = make_float2(0.f, 0.f);
+    V2[o] = make_float2(0.f, 0.f);
+    Vxy[o] = 0.f;
+  }
   float acc = 0.f;
   const float inv49 = 1.0f / 49.0f, cov_norm = 49.0f / 48.0f;
   const float C1 = 0.0004f, C2 = 0.0036f;  // (0.01*2)^2, (0.03*2)^2
+  const float2 inv49_2 = make_float2(inv49, inv49), cov2 = make_float2(cov_norm, cov_norm);
 
   // rows stream global -> shared with cp.async (LDGSTS), STAGES-1 rows in flight; columns beyond the
   // image are zero-filled by the copy itself (src-size 0).  All per-row address arithmetic is kept in
@@ -66,13 +82,13 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
     const bool in = use && (c0 + col) < F;
     coff[u] = in ? col : 0;
     cbytes[u] = in ? 4 : 0;
-    sdst[u] = (unsigned)__cvta_generic_to_shared(&rowbuf[0][0][use ? col : 0]);
+    sdst[u] = (unsigned)__cvta_generic_to_shared(&rowbuf[0][use ? col : 0]);
   }
   const float* e_next = E + (long long)r0 * F + c0;  // row to be issued next
   const float* g_next = G + (long long)r0 * F + c0;
   int rows_left = r_end - r0;
   int stage_next = 0;
-  constexpr unsigned kStageBytes = 2 * RB * sizeof(float), kImgBytes = RB * sizeof(float);
+  constexpr unsigned kStageBytes = RB * sizeof(float2);
   auto issue_row = [&]() {
     if (rows_left > 0) {
       const unsigned sb = stage_next * kStageBytes;
@@ -82,7 +98,7 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst[u] + sb), "l"(e_next + coff[u]),
                        "r"(cbytes[u])
                        : "memory");
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst[u] + sb + kImgBytes),
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst[u] + sb + 4u),
                        "l"(g_next + coff[u]), "r"(cbytes[u])
                        : "memory");
         }
@@ -106,52 +122,45 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
         asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
         __syncthreads();  // row r has landed for everyone; row r-1 is fully consumed
         issue_row();      // refills the stage row r-1 occupied
-        float x[8], y[8];
+        float2 P[8];      // (x, y) of columns c .. c+7
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 xv = *reinterpret_cast<const float2*>(&rowbuf[par][0][c + 2 * j]);
-          const float2 yv = *reinterpret_cast<const float2*>(&rowbuf[par][1][c + 2 * j]);
-          x[2 * j] = xv.x;
-          x[2 * j + 1] = xv.y;
-          y[2 * j] = yv.x;
-          y[2 * j + 1] = yv.y;
+          const float4 v = *reinterpret_cast<const float4*>(&rowbuf[par][c + 2 * j]);
+          P[2 * j] = make_float2(v.x, v.y);
+          P[2 * j + 1] = make_float2(v.z, v.w);
         }
         // inner sums over columns c+1 .. c+6, then the two outputs add their own end column
-        float ix = 0.f, iy = 0.f, ixx = 0.f, iyy = 0.f, ixy = 0.f;
+        float2 S1 = make_float2(0.f, 0.f), S2 = make_float2(0.f, 0.f);
+        float sxy = 0.f;
 #pragma unroll
         for (int j = 1; j < 7; ++j) {
-          ix += x[j];
-          iy += y[j];
-          ixx += x[j] * x[j];
-          iyy += y[j] * y[j];
-          ixy += x[j] * y[j];
+          S1 = add2(S1, P[j]);
+          S2 = fma2(P[j], P[j], S2);
+          sxy = fmaf(P[j].x, P[j].y, sxy);
         }
-        float h[10];
-        h[0] = ix + x[0];
-        h[1] = iy + y[0];
-        h[2] = ixx + x[0] * x[0];
-        h[3] = iyy + y[0] * y[0];
-        h[4] = ixy + x[0] * y[0];
-        h[5] = ix + x[7];
-        h[6] = iy + y[7];
-        h[7] = ixx + x[7] * x[7];
-        h[8] = iyy + y[7] * y[7];
-        h[9] = ixy + x[7] * y[7];
 #pragma unroll
-        for (int q = 0; q < 10; ++q) {
-          V[q] += h[q] - ring[s][q];
-          ring[s][q] = h[q];
+        for (int o = 0; o < 2; ++o) {
+          const float2 pe = P[o == 0 ? 0 : 7];
+          const float2 H1 = add2(S1, pe);
+          const float2 H2 = fma2(pe, pe, S2);
+          const float hxy = fmaf(pe.x, pe.y, sxy);
+          V1[o] = add2(V1[o], sub2(H1, R1[s][o]));
+          V2[o] = add2(V2[o], sub2(H2, R2[s][o]));
+          Vxy[o] += hxy - Rxy[s][o];
+          R1[s][o] = H1;
+          R2[s][o] = H2;
+          Rxy[s][o] = hxy;
         }
         if (r - r0 >= 6) {
 #pragma unroll
           for (int o = 0; o < 2; ++o) {
-            const float ux = V[5 * o] * inv49, uy = V[5 * o + 1] * inv49;
-            const float uxx = V[5 * o + 2] * inv49, uyy = V[5 * o + 3] * inv49, uxy = V[5 * o + 4] * inv49;
-            const float vx = cov_norm * (uxx - ux * ux);
-            const float vy = cov_norm * (uyy - uy * uy);
-            const float vxy = cov_norm * (uxy - ux * uy);
-            const float A1 = 2.f * ux * uy + C1, A2 = 2.f * vxy + C2;
-            const float B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+            const float2 u1 = mul2(V1[o], inv49_2);                    // (ux, uy)
+            const float2 u2 = mul2(V2[o], inv49_2);                    // (uxx, uyy)
+            const float uxy = Vxy[o] * inv49;
+            const float2 var = mul2(cov2, fma2(make_float2(-u1.x, -u1.y), u1, u2));  // (vx, vy)
+            const float vxy = cov_norm * (uxy - u1.x * u1.y);
+            const float A1 = 2.f * u1.x * u1.y + C1, A2 = 2.f * vxy + C2;
+            const float B1 = u1.x * u1.x + u1.y * u1.y + C1, B2 = var.x + var.y + C2;
             const float S = __fdividef(A1 * A2, B1 * B2);
             if (o == 0 ? ok0 : ok1) acc += S;
           }
