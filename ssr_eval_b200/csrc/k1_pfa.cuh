@@ -219,7 +219,13 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
           b3b[q] = b[q];
         }
         __syncthreads();
-        // ---- inverse pass 2
+        // ---- inverse pass 2 (the chirp * W_N^{rk} factors of the output stage are pulled towards L1 meanwhile:
+        // they are L2 round trips otherwise, and holding them in registers across two passes would spill)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int k = tid + 128 * q;
+          if (k < P) prefetch_l1(D.post + r * P + k);
+        }
         v[0] = b2[0];
 #pragma unroll
         for (int q = 1; q < 16; ++q) v[q] = cmul_conj(b2[9 * q], t2[(q - 1) * 8]);

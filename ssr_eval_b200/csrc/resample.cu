@@ -61,70 +61,75 @@ k_resample(const T* __restrict__ x, const long long* __restrict__ in_off, T* __r
 // The float32 multiply / add order per output is unchanged (ascending input index), so results stay
 // bit-identical to scipy.
 // EXACT: K == KMAX (the common ratios get their own instantiation, so the unrolled tap loops carry no run-time
-// `k < K` predicates and no dead iterations)
+// `k < K` predicates and no dead iterations).
+// The input span a CTA needs ((TP*R - 1) * down / up + K samples, 9-19 KB) is staged in shared memory first,
+// zero-filled outside the utterance: scipy's zero extension then needs no bounds logic (adding x*h with x = 0
+// leaves the float32 sum unchanged), and the ~21 loads per output are LDS instead of LDG -- the global-load
+// instruction queue was what bound the first version (ncu: lg_throttle 4.0, long_scoreboard 5.4 warps / issue).
 template <int KMAX, int R, bool EXACT>
 __global__ void __launch_bounds__(512)
 k_resample_tiled(const float* __restrict__ x, const long long* __restrict__ in_off, float* __restrict__ y,
                  const long long* __restrict__ out_off, int u0, int up, int down, int n_pre_pad,
-                 int n_pre_remove, int K, const float* __restrict__ bank) {
+                 int n_pre_remove, int K, const float* __restrict__ bank, int span) {
+  extern __shared__ float xs[];
   const int u = u0 + blockIdx.y;
   const long long n_out = out_off[u + 1] - out_off[u];
   const int TP = blockDim.x;
-  const long long j0 = (long long)blockIdx.x * TP * R + threadIdx.x;
-  if ((long long)blockIdx.x * TP * R >= n_out) return;
+  const long long jb = (long long)blockIdx.x * TP * R;  // first output of this CTA
+  if (jb >= n_out) return;
   const long long n_in = in_off[u + 1] - in_off[u];
   const float* xu = x + in_off[u];
   float* yu = y + out_off[u];
-  long long c = (j0 + n_pre_remove) * (long long)down - n_pre_pad;
-  long long i_hi = c / up;
-  long long phase = c - i_hi * up;
-  if (phase < 0) {
-    phase += up;
-    i_hi -= 1;
+  // input index of the newest sample of output j: floor(((j + n_pre_remove) * down - n_pre_pad) / up)
+  auto newest = [&](long long j, long long* phase) {
+    const long long c = (j + n_pre_remove) * (long long)down - n_pre_pad;
+    long long i = c / up;
+    long long ph = c - i * up;
+    if (ph < 0) {  // floor division for negative c
+      ph += up;
+      i -= 1;
+    }
+    *phase = ph;
+    return i;
+  };
+  long long ph0;
+  const long long i_base = newest(jb, &ph0) - (K - 1);  // oldest sample the CTA touches
+  for (int i = threadIdx.x; i < span; i += TP) {
+    const long long gi = i_base + i;
+    xs[i] = (gi >= 0 && gi < n_in) ? __ldg(xu + gi) : 0.f;
   }
+  __syncthreads();
+
+  const long long j0 = jb + threadIdx.x;
+  long long phase;
+  const int p0 = (int)(newest(j0, &phase) - i_base);  // index of the newest sample of output j0 inside xs
   float h[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) h[k] = (EXACT || k < K) ? __ldg(bank + phase * K + k) : 0.f;
-  const long long step = (long long)(TP / up) * down;  // input advance per TP outputs (TP % up == 0)
+  const int step = (TP / up) * down;  // input advance per TP outputs (TP % up == 0)
   // G outputs are accumulated together: G independent float32 add chains and G*K loads in flight
   constexpr int G = 4;
   static_assert(R % G == 0, "R must be a multiple of G");
 #pragma unroll 1
   for (int i0 = 0; i0 < R; i0 += G) {
     float acc[G];
-    bool inner[G], live[G];
     const float* px[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const long long ih = i_hi + (long long)g * step;
       acc[g] = 0.f;
-      live[g] = (j0 + (long long)(i0 + g) * TP) < n_out;
-      inner[g] = live[g] && ih - (K - 1) >= 0 && ih < n_in;
-      px[g] = xu + ih;
+      px[g] = xs + p0 + (i0 + g) * step;
     }
-    if (inner[0] && inner[1] && inner[2] && inner[3]) {  // interior: no bounds checks
 #pragma unroll
-      for (int k = KMAX - 1; k >= 0; --k)
-        if (EXACT || k < K) {
+    for (int k = KMAX - 1; k >= 0; --k)
+      if (EXACT || k < K) {
 #pragma unroll
-          for (int g = 0; g < G; ++g) acc[g] = __fadd_rn(acc[g], __fmul_rn(__ldg(px[g] - k), h[k]));
-        }
-    } else {
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (!live[g]) continue;
-        const long long ih = i_hi + (long long)g * step;
-#pragma unroll
-        for (int k = KMAX - 1; k >= 0; --k) {
-          const long long ii = ih - k;
-          if ((EXACT || k < K) && ii >= 0 && ii < n_in) acc[g] = __fadd_rn(acc[g], __fmul_rn(__ldg(xu + ii), h[k]));
-        }
+        for (int g = 0; g < G; ++g) acc[g] = __fadd_rn(acc[g], __fmul_rn(px[g][-k], h[k]));
       }
-    }
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-      if (live[g]) yu[j0 + (long long)(i0 + g) * TP] = acc[g];
-    i_hi += (long long)G * step;
+    for (int g = 0; g < G; ++g) {
+      const long long j = j0 + (long long)(i0 + g) * TP;
+      if (j < n_out) yu[j] = acc[g];
+    }
   }
 }
 
@@ -243,17 +248,21 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // tiled kernel: block = smallest multiple of `up` that is >= 256 threads (<= 512), 8 outputs per thread
   int TP = plan->up * ((256 + plan->up - 1) / plan->up);
-  if (TP <= 512 && plan->K <= 48) {
-    constexpr int R = 8;
+  constexpr int R = 8;
+  // input samples one CTA touches: newest(j_last) - newest(j_first) + K <= (TP*R - 1) * down / up + 1 + K
+  const long long span_ll = ((long long)TP * R - 1) * plan->down / plan->up + 2 + plan->K;
+  if (TP <= 512 && plan->K <= 48 && span_ll * (long long)sizeof(float) <= 48 * 1024) {
+    const int span = (int)span_ll;
+    const size_t smem = sizeof(float) * (size_t)span;
     for (int u0 = 0; u0 < n; u0 += 32768) {
       int nu = n - u0 < 32768 ? n - u0 : 32768;
       dim3 grid((unsigned)((max_out + (long long)TP * R - 1) / ((long long)TP * R)), nu);
       const long long* io = reinterpret_cast<const long long*>(in_offsets_dev);
       const long long* oo = reinterpret_cast<const long long*>(out_offsets_dev);
 #define SSR_K3_LAUNCH(KM, EX)                                                                              \
-  k_resample_tiled<KM, R, EX><<<grid, TP, 0, st>>>(x_dev, io, y_dev, oo, u0, plan->up, plan->down,        \
-                                                   plan->n_pre_pad, plan->n_pre_remove, plan->K,          \
-                                                   static_cast<const float*>(plan->bank))
+  k_resample_tiled<KM, R, EX><<<grid, TP, smem, st>>>(x_dev, io, y_dev, oo, u0, plan->up, plan->down,     \
+                                                      plan->n_pre_pad, plan->n_pre_remove, plan->K,       \
+                                                      static_cast<const float*>(plan->bank), span)
       if (plan->K == 21) SSR_K3_LAUNCH(21, true);       // 44.1k <-> 48k up (160/147), 16k -> 44.1k (441/160)
       else if (plan->K == 22) SSR_K3_LAUNCH(22, true);  // 48k -> 44.1k (147/160)
       else if (plan->K <= 24) SSR_K3_LAUNCH(24, false);
