@@ -23,7 +23,7 @@ k_stft_metrics(StftDev P, const ET* __restrict__ est, const float* __restrict__ 
                const long long* __restrict__ offsets, const int* __restrict__ item_start,
                const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
                double* __restrict__ partials, float* __restrict__ spec_e,
-               float* __restrict__ spec_t, const long long* __restrict__ spec_off) {
+               float* __restrict__ spec_t, const long long* __restrict__ spec_off, int* __restrict__ next_item) {
   constexpr int M = 1 << LOGM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* buf = reinterpret_cast<cd*>(smem_raw);
@@ -37,7 +37,8 @@ k_stft_metrics(StftDev P, const ET* __restrict__ est, const float* __restrict__ 
   const bool want_lsd = flags & SSR_METRIC_LSD, want_log = flags & SSR_METRIC_LOG_SISPEC,
              want_lin = flags & SSR_METRIC_SISPEC;
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  __shared__ int item_slot;
+  for (int item = next_work_item(next_item, &item_slot); item < n_items; item = next_work_item(next_item, &item_slot)) {
     const int p = item_pair[item];
     const int c = item - item_start[p];
     const long long off = offsets[p];

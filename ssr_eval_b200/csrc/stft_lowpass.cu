@@ -227,19 +227,38 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
   for (int i = tid; i < span; i += kV2Threads) acc[i] = 0.f;
   __syncthreads();
 
+  // samples of the NEXT interior frame pair, loaded while the current pair is transformed (32 registers);
+  // the analysis window is wn * N exactly (N is a power of two), so it costs a multiply instead of 16 loads
+  float nx0[16], nx1[16];
+  long long nx_f = -1;  // frame pair the prefetched samples belong to
+  auto prefetch_pair = [&](long long f) {
+    const long long s0 = f * hop - N / 2, s1 = s0 + hop;
+    if (f <= f_hi && s0 >= 0 && s1 + N <= L) {
+      const bool two = (f + 1) <= f_hi;
+      const float* p0 = xu + s0 + tid;
+      const float* p1 = xu + s1 + tid;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        nx0[r] = __ldg(p0 + 128 * r);
+        nx1[r] = two ? __ldg(p1 + 128 * r) : 0.f;
+      }
+      nx_f = f;
+    }
+  };
+  prefetch_pair(f_lo);
+
   for (long long f = f_lo; f <= f_hi; f += 2) {
     const bool two = (f + 1) <= f_hi;
     const long long s0 = f * hop - N / 2, s1 = s0 + hop;
     cf v[16];
     // ---- forward pass 1: z = w*x_f + i*w*x_{f+1}
-    if (s0 >= 0 && s1 + N <= L) {
-      const float* p0 = xu + s0 + tid;
-      const float* p1 = xu + s1 + tid;
+    if (nx_f == f) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        const float w = __ldg(P.win + tid + 128 * r);
-        v[r] = cf{w * __ldg(p0 + 128 * r), two ? w * __ldg(p1 + 128 * r) : 0.f};
+        const float w = wn[r] * (float)N;
+        v[r] = cf{w * nx0[r], w * nx1[r]};
       }
+      prefetch_pair(f + 2);
     } else {
       // edge frame pair (reflect padding): gather through the FFT buffer (free here: the previous
       // pair's inverse-pass-3 loads were followed by two barriers) to keep 64-bit reflect math out of
@@ -253,11 +272,12 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
       __syncthreads();
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        const float w = __ldg(P.win + tid + 128 * r);
+        const float w = wn[r] * (float)N;
         const cf raw = buf[tid + 128 * r];
         v[r] = cf{w * raw.x, w * raw.y};
       }
       __syncthreads();  // all raw values are in registers before pass 1 overwrites the buffer
+      prefetch_pair(f + 2);
     }
     bfly16<false>(v);
     b1[0] = v[0];

@@ -135,7 +135,7 @@ static int launch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStrea
                      const ET* est, const float* tgt, const long long* offs_dev,
                      const int* item_start, const int* item_pair, int n_items, int chunk,
                      unsigned flags, double* partials, float* spec_e, float* spec_t,
-                     const long long* spec_off) {
+                     const long long* spec_off, int* next_item) {
   auto kern = k_stft_metrics<LOGM, BLUE, ET>;
   SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TimingState& tm = timing();
@@ -151,7 +151,7 @@ static int launch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStrea
     SSR_CUDA_TRY(cudaEventRecord(ev.first, st));
   }
   kern<<<grid, kThreads, smem, st>>>(plan->dev, est, tgt, offs_dev, item_start, item_pair, n_items,
-                                     chunk, flags, partials, spec_e, spec_t, spec_off);
+                                     chunk, flags, partials, spec_e, spec_t, spec_off, next_item);
   SSR_LAUNCH_CHECK("k_stft_metrics");
   if (tm.on) {
     SSR_CUDA_TRY(cudaEventRecord(ev.second, st));
@@ -165,11 +165,11 @@ static int dispatch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStr
                        const ET* est, const float* tgt, const long long* offs_dev,
                        const int* item_start, const int* item_pair, int n_items, int chunk,
                        unsigned flags, double* partials, float* spec_e, float* spec_t,
-                       const long long* spec_off) {
+                       const long long* spec_off, int* next_item) {
 #define SSR_CASE(LM)                                                                            \
   case LM:                                                                                      \
     return launch_k1<LM, BLUE, ET>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair, \
-                               n_items, chunk, flags, partials, spec_e, spec_t, spec_off);
+                               n_items, chunk, flags, partials, spec_e, spec_t, spec_off, next_item);
   switch (plan->logM) {
     SSR_CASE(8)
     SSR_CASE(9)
@@ -206,9 +206,9 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   if (est64) {
     if (plan->bluestein)
       return dispatch_k1<true, double>(plan, grid, smem, st, est64, tgt, offs_dev, item_start, item_pair,
-                                       w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off);
+                                       w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
     return dispatch_k1<false, double>(plan, grid, smem, st, est64, tgt, offs_dev, item_start, item_pair,
-                                      w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off);
+                                      w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
   }
   if (plan->pfa && !force_generic_k1()) {
     const size_t smem_p = sizeof(cd) * (2048 + 256) + sizeof(cd) * (size_t)(plan->n_fft - plan->pdev.P);
@@ -292,9 +292,9 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   }
   if (plan->bluestein)
     return dispatch_k1<true, float>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair,
-                             w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off);
+                             w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
   return dispatch_k1<false, float>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair,
-                            w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off);
+                            w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
 }
 
 }  // namespace ssr
