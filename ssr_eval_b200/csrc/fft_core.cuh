@@ -47,6 +47,31 @@ template <typename T>
 SSR_HD C2<T> csub(C2<T> a, C2<T> b) {
   return C2<T>{a.x - b.x, a.y - b.y};
 }
+// float32 complex add / sub on sm_100: the (re, im) pair is one 64-bit register pair, so FADD2 (PTX add / sub
+// .rn.f32x2) does both halves in one instruction -- same IEEE roundings, half the issue slots (K4's float32 FFT)
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+template <>
+__device__ __forceinline__ C2<float> cadd<float>(C2<float> a, C2<float> b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  C2<float> d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+template <>
+__device__ __forceinline__ C2<float> csub<float>(C2<float> a, C2<float> b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  C2<float> d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+#endif
+
 // multiply by -i (forward) or +i (inverse)
 template <bool INV, typename T>
 SSR_HD C2<T> mul_mi(C2<T> v) {
