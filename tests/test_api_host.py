@@ -156,3 +156,52 @@ def test_reference_methods_live_when_the_reference_is_mounted(tmp_path):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_per_family_degradation_methods_keys_and_calls(tmp_path, monkeypatch):
+    """lowpass_butterworth / _chebyshev / _ellip / _bessel / _subsampling / _stft_hard (ssr_eval/eval.py:334-421):
+    key naming, the `low_rate == sr -> low_rate - 1` rule and the arguments handed to the filters, with the GPU
+    entry points replaced by recorders (host logic only)."""
+    import ssr_eval_b200.eval as ev
+    calls = []
+
+    def fake_lowpass_batch(waves, highcut, fs, order=5, _type="butter"):
+        calls.append(("lowpass", len(waves), highcut, fs, order, _type))
+        return [np.asarray(w) * 0.5 for w in waves]
+
+    def fake_hard(waves, ratios):
+        calls.append(("stft_hard", len(waves), [round(r, 6) for r in ratios]))
+        return [np.asarray(w) * 0.25 for w in waves]
+
+    monkeypatch.setattr(ev, "lowpass_batch", fake_lowpass_batch)
+    monkeypatch.setattr(ev, "stft_hard_lowpass_batch", fake_hard)
+    h = SSR_Eval_Helper(BasicTestee(), 44100, 44100, test_data_root=str(tmp_path),
+                        setting_fft={"cutoff_freq": [4000, 22050]}, setting_subsampling={"cutoff_freq": [8000]},
+                        setting_lowpass_filtering={"filter": ["butter", "cheby", "ellip", "bessel"],
+                                                   "cutoff_freq": [6000], "filter_order": [2, 8]})
+    x = np.linspace(-1, 1, 1000).astype(np.float32)
+    d = h.lowpass_butterworth("f.wav", x, 44100)
+    assert list(d) == ["proc_bw_12000_2_44100", "proc_bw_12000_8_44100"]
+    assert calls == [("lowpass", 1, 6000, 44100, 2, "butter"), ("lowpass", 1, 6000, 44100, 8, "butter")]
+    calls.clear()
+    assert list(h.lowpass_chebyshev("f.wav", x, 44100)) == ["proc_ch_12000_2_44100", "proc_ch_12000_8_44100"]
+    assert [c[5] for c in calls] == ["cheby1", "cheby1"]
+    assert list(h.lowpass_ellip("f.wav", x, 44100)) == ["proc_el_12000_2_44100", "proc_el_12000_8_44100"]
+    assert list(h.lowpass_bessel("f.wav", x, 44100)) == ["proc_bessel_12000_2_44100", "proc_bessel_12000_8_44100"]
+    calls.clear()
+    assert list(h.lowpass_subsampling("f.wav", x, 44100)) == ["proc_subsampling_16000_44100"]
+    assert calls == [("lowpass", 1, 8000, 44100, 1, "subsampling")]
+    calls.clear()
+    d = h.lowpass_stft_hard("f.wav", x, 44100)
+    # doubled cutoff 44100 == sr -> 44099 (eval.py:404-405); ratio = (low_rate // 2) / int(sr / 2)
+    assert list(d) == ["proc_fft_8000_44100", "proc_fft_44099_44100"]
+    assert calls == [("stft_hard", 2, [round(4000 / 22050, 6), round(22049 / 22050, 6)])]
+    # preprocess-style fan-out: every family present, reference order (filters, subsampling, fft)
+    calls.clear()
+    full = h._degrade_batch([x, x[:500]], 44100)
+    assert [list(o) for o in full] == [list(full[0])] * 2
+    assert list(full[0]) == ["proc_bw_12000_2_44100", "proc_bw_12000_8_44100", "proc_ch_12000_2_44100",
+                             "proc_ch_12000_8_44100", "proc_el_12000_2_44100", "proc_el_12000_8_44100",
+                             "proc_bessel_12000_2_44100", "proc_bessel_12000_8_44100",
+                             "proc_subsampling_16000_44100", "proc_fft_8000_44100", "proc_fft_44099_44100"]
+    assert all(c[1] == 2 for c in calls if c[0] == "lowpass") and calls[-1][1] == 4
