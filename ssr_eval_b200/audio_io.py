@@ -26,15 +26,25 @@ def write_wav(path, x, sr):
     wavfile.write(path, int(sr), np.asarray(x, dtype=np.float32))
 
 
-def load_audio(path, sr=None):
-    """Mono float32 load with optional rate conversion (librosa.load(path, sr=sr) stand-in)."""
+def load_audio(path, sr=None, res_type="polyphase"):
+    """Mono float32 load with optional rate conversion (librosa.load(path, sr=sr) stand-in).  ``res_type``:
+    "polyphase" (scipy resample_poly's Kaiser-5.0 FIR, the default here) or "kaiser_best" (the band-limited
+    Kaiser-windowed sinc librosa 0.9 defaults to; same K3 kernel, different taps -- see engine.kaiser_best_taps)."""
     if not str(path).lower().endswith(".wav"):
         raise ValueError("only .wav files are supported in this image (no soundfile/flac codec): %s" % path)
     x, native = read_wav(path)
     if sr is None or int(sr) == native:
         return x, native
-    from .engine import PolyphaseResampler
-    y = PolyphaseResampler(int(sr), native).resample([x])[0]
+    from math import gcd
+    from .engine import PolyphaseResampler, kaiser_best_taps
+    if res_type == "polyphase":
+        rs = PolyphaseResampler(int(sr), native)
+    elif res_type == "kaiser_best":
+        g = gcd(int(sr), native)
+        rs = PolyphaseResampler(int(sr), native, taps=kaiser_best_taps(int(sr) // g, native // g))
+    else:
+        raise ValueError("res_type must be 'polyphase' or 'kaiser_best', got %r" % (res_type,))
+    y = rs.resample([x])[0]
     n = int(np.ceil(len(x) * float(sr) / native))
     if len(y) > n:
         y = y[:n]

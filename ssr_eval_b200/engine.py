@@ -181,11 +181,30 @@ def resample_poly_taps(up, down, dtype=np.float32):
     return h
 
 
+def kaiser_best_taps(up, down, dtype=np.float32, num_zeros=64, rolloff=0.9475937167399596, beta=14.769656459379492):
+    """Prototype FIR of a band-limited (Kaiser-windowed sinc) resampler with resampy's ``kaiser_best`` parameters
+    (64 zero crossings, roll-off 0.9476, beta 14.77 -- what librosa 0.9's ``librosa.load(sr=...)`` uses), sampled on
+    the polyphase grid of ``resample_poly(x, up, down)`` and already scaled like scipy's ``h * up``:
+    taps[m + M] = g(m / up), g(t) = c * sinc(c t) * kaiser(c t / num_zeros), c = min(1, up / down) * rolloff, t in
+    input samples.  PARITY UNPINNED: resampy itself interpolates a 512-per-zero-crossing table of this kernel
+    linearly; this is the exact kernel (torchaudio documents the same parameters as its kaiser_best equivalent)."""
+    up, down = int(up), int(down)
+    c = min(1.0, up / down) * rolloff
+    half = int(np.ceil(num_zeros / c * up))  # support |c t| <= num_zeros
+    t = np.arange(-half, half + 1, dtype=np.float64) / up
+    u = np.clip(c * t / num_zeros, -1.0, 1.0)
+    win = np.i0(beta * np.sqrt(1.0 - u * u)) / np.i0(beta)
+    win[np.abs(c * t) > num_zeros] = 0.0
+    return (c * np.sinc(c * t) * win).astype(dtype)
+
+
 class PolyphaseResampler:
     """K3: scipy.signal.resample_poly(x, up, down) for float32 batches (dtype=np.float64: float64 batches --
     scipy keeps the input dtype, so a float64 waveform is filtered with float64 taps in float64)."""
 
-    def __init__(self, up, down, dtype=np.float32):
+    def __init__(self, up, down, dtype=np.float32, taps=None):
+        """``taps``: optional prototype FIR (odd length, already scaled like scipy's ``h * up``) instead of the
+        Kaiser-5.0 ``firwin`` design of resample_poly, e.g. ``kaiser_best_taps(up, down)``."""
         _require_cuda()
         g = gcd(int(up), int(down))
         self.up, self.down = int(up) // g, int(down) // g
@@ -195,7 +214,10 @@ class PolyphaseResampler:
         self._tdtype = torch.float64 if self.dtype == np.float64 else torch.float32
         self._plan = ctypes.c_void_p()
         if not self.identity:
-            taps = np.ascontiguousarray(resample_poly_taps(self.up, self.down, dtype=self.dtype))
+            if taps is None:
+                taps = resample_poly_taps(self.up, self.down, dtype=self.dtype)
+            taps = np.ascontiguousarray(taps, dtype=self.dtype)
+            assert taps.ndim == 1 and len(taps) % 2 == 1
             create = N.lib().ssr_resample_plan_create_f64 if self.dtype == np.float64 else N.lib().ssr_resample_plan_create
             N.check(create(ctypes.byref(self._plan), self.up, self.down, _np_ptr(taps), len(taps)),
                     "ssr_resample_plan_create")

@@ -64,6 +64,10 @@ class BasicTestee:
 
 
 class SSR_Eval_Helper:
+    # resampler used when a file's native rate differs from input_sr / evaluation_sr ("polyphase" | "kaiser_best");
+    # the reference leaves this to librosa.load (kaiser_best in 0.9) and to the sox binary -- see INTEGRATION.md
+    load_res_type = "polyphase"
+
     def __init__(self, testee, input_sr, output_sr, evaluation_sr=44100, test_name="test",
                  test_data_root="./datasets/vctk_test", setting_lowpass_filtering=None,
                  setting_subsampling=None, setting_fft=None, setting_mp3_compression=None,
@@ -142,7 +146,7 @@ class SSR_Eval_Helper:
         return outs
 
     def preprocess(self, file, sr):
-        x, _ = load_audio(file, sr=sr)
+        x, _ = load_audio(file, sr=sr, res_type=self.load_res_type)
         return self._degrade_batch([x], sr)[0]
 
     # The reference's per-family degradation methods (eval.py:334-421), same names, arguments and keys; `file`
@@ -233,8 +237,8 @@ class SSR_Eval_Helper:
 
     def evaluate_batch(self, files):
         """{file: {key: {metric: float}}} for a list of audio paths -- one launch sequence."""
-        xs = [load_audio(f, sr=self.model_input_sr)[0] for f in files]
-        targets = [load_audio(f, sr=self.evaluationset_sr)[0] for f in files]
+        xs = [load_audio(f, sr=self.model_input_sr, res_type=self.load_res_type)[0] for f in files]
+        targets = [load_audio(f, sr=self.evaluationset_sr, res_type=self.load_res_type)[0] for f in files]
         degraded = self._degrade_batch(xs, self.model_input_sr)
         items, processed, extras = [], [], []
         for fi, d in enumerate(degraded):

@@ -569,3 +569,28 @@ def test_fuzz_stft_sizes_and_ragged_batches_vs_oracle():
             if want["sispec"] > 60:  # (near-)identical pair: the reference's own float32 cancellation noise
                 tol.pop("sispec")
             _assert_metrics(dict(zip(METRICS, got[i])), want, f"case {case} n_fft {n_fft} hop {hop} L {L} {est[i].dtype}", tol)
+
+
+def test_kaiser_best_load_resampler_vs_scipy_with_the_same_taps(tmp_path):
+    """load_audio(res_type="kaiser_best"): the K3 kernel with a Kaiser-windowed-sinc prototype (engine.kaiser_best_taps)
+    instead of resample_poly's firwin design -- bit-exact against scipy's upfirdn fed the same float32 taps (K = 136 ..
+    407 taps per output: the one-output-per-thread kernel), and within float32 rounding of torchaudio's documented
+    kaiser_best equivalent (tests/test_oracle.py checks the design itself on the CPU)."""
+    from scipy.io import wavfile
+    from ssr_eval_b200.audio_io import load_audio
+    from ssr_eval_b200.engine import PolyphaseResampler, kaiser_best_taps
+    for orig, new, L in ((48000, 44100, 30000), (48000, 16000, 24001), (16000, 44100, 9000)):
+        g = int(np.gcd(orig, new))
+        up, down = new // g, orig // g
+        x = speech_like(L, orig, seed=orig // 1000 + new // 1000)
+        w32 = (kaiser_best_taps(up, down, dtype=np.float64) / up).astype(np.float32)
+        want = resample_poly(x, up, down, window=w32.copy())          # scipy: h = window * up, float32 upfirdn
+        got = PolyphaseResampler(up, down, taps=w32 * np.float32(up)).resample([x])[0]
+        assert got.dtype == np.float32 and got.shape == want.shape
+        assert np.array_equal(got, want), (orig, new, np.abs(got - want).max())
+    wavfile.write(str(tmp_path / "a.wav"), 48000, speech_like(20000, 48000, seed=5))
+    y, sr = load_audio(str(tmp_path / "a.wav"), sr=44100, res_type="kaiser_best")
+    z, _ = load_audio(str(tmp_path / "a.wav"), sr=44100)
+    assert sr == 44100 and len(y) == len(z) == 18375 and np.abs(y - z).max() > 1e-4  # two different filters
+    with pytest.raises(ValueError):
+        load_audio(str(tmp_path / "a.wav"), sr=44100, res_type="sinc")
