@@ -26,13 +26,20 @@ Pinning status (see DESIGN.md, section "Oracle")
   ``ssr_eval.metrics.AudioMetrics`` / ``ssr_eval.lowpass.lowpass`` /
   ``ssr_eval.utils.dict_mean`` code from ``/root/reference`` (script:
   ``tests/golden/make_golden.py``) with the missing third-party packages replaced by the
-  shims in ``oracle/shims`` (which are built from this restatement).
+  shims in ``oracle/shims`` (which are built from this restatement).  The orchestration
+  (distortion fan-out and key naming, plugin call, output resampling, float64 handling,
+  per-speaker means and mean of means) is PINNED the same way by running the reference's own
+  ``SSR_Eval_Helper.evaluate()`` (``tests/golden/make_golden_helper.py`` ->
+  ``tests/golden/helper_reference_runs.json``), and ``tests/test_reference_live.py`` re-runs
+  the reference's metrics / lowpass code against this package on random cases whenever
+  ``/root/reference`` is mounted.
 * ``scipy.signal.resample_poly``: PINNED by the installed scipy (called directly).
 * ``librosa.stft`` framing / ``skimage...structural_similarity`` / ``torchlibrosa``
   STFT+ISTFT / ``librosa.resample`` wrapper: PARITY UNPINNED by any test or fixture of the
   reference (it has none); restated from the documented behaviour of the
   era-consistent versions and cross-checked against independent implementations
-  (``torch.stft`` in float64, brute-force SSIM, ``numpy.fft.irfft`` overlap-add).
+  (``torch.stft`` in float64 and torchaudio's librosa-compatible ``Spectrogram``, brute-force
+  SSIM and an OpenCV box filter, ``numpy.fft.irfft`` overlap-add).
 """
 from .stft import hann_periodic, stft_complex, stft_mag, n_frames  # noqa: F401
 from .metrics import (  # noqa: F401
