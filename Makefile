@@ -5,7 +5,7 @@ NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-f
 SRC := ssr_eval_b200/csrc
 OBJ := build/obj
 LIB := ssr_eval_b200/lib/libssr_b200.so
-SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu $(SRC)/stft_splice.cu $(SRC)/sosfiltfilt.cu
+SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu $(SRC)/stft_splice.cu $(SRC)/sosfiltfilt.cu $(SRC)/pcm.cu
 OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(SRCS))
 HDRS := $(wildcard $(SRC)/*.cuh) $(SRC)/stft_tables.hpp include/ssr_b200.h
 

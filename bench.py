@@ -308,26 +308,47 @@ def run_gpu(args):
     value = world * n_pairs * args.steps / (ms * 1e-3)
     lsd_mean = float(out[:, 0].mean().item())
 
-    # ---- end to end through the public host API: pinned host buffers -> H2D -> kernels -> D2H
+    # ---- end to end through the public host API: pinned host buffers -> H2D -> kernels -> D2H.
+    # Headline e2e: the host batch is 16-bit PCM -- the sample format of the wav files the reference reads
+    # (VCTK, and everything it writes with sf.write); librosa.load turns a sample s into float32(s) / 32768, which
+    # is what K0 does on the device after a 2-byte-per-sample upload.  The same batch as float32 host buffers
+    # (4 bytes per sample over PCIe) is timed too and reported as e2e_f32_host.
     from ssr_eval_b200.engine import HostPipeline
+    pipe = HostPipeline(eng, n_pairs, LENGTH)
+
+    def to_pcm16(x):
+        return torch.clamp(torch.round(x * 32768.0), -32768, 32767).to(torch.int16)
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def time_e2e(est_h, tgt_h):
+        pipe.run(est_h, tgt_h, off, flags)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r = pipe.run(est_h, tgt_h, off, flags)
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(tt, op=td.ReduceOp.MAX)
+        return world * n_pairs * e2e_steps / float(tt.item()), r
+
+    est_q, tgt_q = to_pcm16(est), to_pcm16(tgt)
+    # device-resident result of the very same (dequantised) pairs, for the equality check below
+    want_q = eng.metrics_device(est_q.float() / 32768.0, tgt_q.float() / 32768.0, off, flags, offsets_dev=off_dev)
+    want_q = want_q.cpu().numpy()
+    est_qh, tgt_qh = est_q.cpu().pin_memory(), tgt_q.cpu().pin_memory()
+    del est_q, tgt_q
+    e2e_value, res = time_e2e(est_qh, tgt_qh)
+    assert np.array_equal(res[:, 0], want_q[:, 0]), "e2e (PCM16 host buffers) differs from the device-resident run"
+    del est_qh, tgt_qh
     est_h = est.cpu().pin_memory()
     tgt_h = tgt.cpu().pin_memory()
-    pipe = HostPipeline(eng, n_pairs, LENGTH)
-    pipe.run(est_h, tgt_h, off, flags)  # warm
-    barrier()
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = pipe.run(est_h, tgt_h, off, flags)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    e2e_value = world * n_pairs * e2e_steps / float(t.item())
+    e2e_f32_value, res32 = time_e2e(est_h, tgt_h)
+    assert abs(float(np.mean(res32[:, 0])) - lsd_mean) < 1e-9
+    del est_h, tgt_h
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    assert abs(float(np.mean(res[:, 0])) - lsd_mean) < 1e-9
 
     # ---- context numbers (not part of the contract metric): the reference's own per-pair call computes all four
     # metrics, and at 48 kHz its STFT is n_fft 2229 / hop 480 (metrics.py:18-19); same device-resident batch
@@ -350,6 +371,26 @@ def run_gpu(args):
                   "n_fft2229_hop480_lsd": rate(eng48, N.METRIC_LSD, 2),
                   "n_fft2229_hop480_all_four_metrics": rate(eng48, N.METRIC_ALL, 2)}
         del eng48
+
+    check = {"mean_lsd": lsd_mean}
+    if rank == 0 and not args.no_oracle_check:
+        # parity inside the run: two pairs of the timed batch (pair 0: hard-low-passed estimate) scored by the CPU
+        # oracle -- the checker, outside every timed region -- against the values the timed kernels produced
+        import oracle
+        got_all = eng.metrics_device(est[:2 * LENGTH], tgt[:2 * LENGTH], off[:3], N.METRIC_ALL).cpu().numpy()
+        timed = out[:2].cpu().numpy()
+        diffs = {m: 0.0 for m in N.METRIC_NAMES}
+        for i in range(2):
+            e_i = est[i * LENGTH:(i + 1) * LENGTH].cpu().numpy()
+            t_i = tgt[i * LENGTH:(i + 1) * LENGTH].cpu().numpy()
+            want = oracle.evaluation(e_i, t_i, n_fft=N_FFT, hop=HOP)
+            assert got_all[i, 0] == timed[i, 0], "LSD of the timed launch and of the all-metrics launch differ"
+            for j, m in enumerate(N.METRIC_NAMES):
+                diffs[m] = max(diffs[m], abs(float(got_all[i, j]) - float(want[m])))
+        check["oracle_pairs"] = 2
+        check["max_abs_diff"] = diffs
+        check["tolerance"] = {"lsd": 1e-4, "log_sispec": 1e-4, "ssim": 1e-3}
+        check["ok"] = bool(diffs["lsd"] <= 1e-4 and diffs["ssim"] <= 1e-3)
 
     if rank == 0:
         peaks = {}
@@ -390,12 +431,15 @@ def run_gpu(args):
                        "pairs_per_gpu": n_pairs, "sample_rate": SR, "length": LENGTH, "n_fft": N_FFT, "hop": HOP,
                        "l2_policy": "inputs (1.97 GB/GPU) larger than L2, no flush", "parallelism": "pairs sharded, 1 all-reduce"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * n_pairs * LENGTH * 4),
-                    "d2h_bytes_per_step": int(n_pairs * 4 * 8), "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * n_pairs * LENGTH * 2),
+                    "d2h_bytes_per_step": int(n_pairs * 4 * 8), "steps": e2e_steps,
+                    "host_format": "int16 PCM (wav sample format), converted on the device (K0)"},
+            "e2e_f32_host": {"value": e2e_f32_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * n_pairs * LENGTH * 4),
+                             "d2h_bytes_per_step": int(n_pairs * 4 * 8), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "check": {"mean_lsd": lsd_mean},
+            "check": check,
             "extras": extras,
         }
         print(json.dumps(line), flush=True)
@@ -413,6 +457,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-pairs-per-core", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-oracle-check", action="store_true", help="skip the two-pair CPU-oracle parity check")
     ap.add_argument("--no-extras", action="store_true", help="skip the context measurements (all four metrics, n_fft 2229)")
     args = ap.parse_args()
     if args.impl == "reference":

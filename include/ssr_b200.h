@@ -169,6 +169,13 @@ int ssr_sosfiltfilt_batched(const double* sos_host, int n_sections, const double
                             const float* x_dev, const int64_t* offsets_host, const int64_t* offsets_dev,
                             int n, double* y_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K0: 16-bit PCM -> float32, dst[i] = (float)src[i] / 32768 -- what librosa.load / soundfile.read hand the
+ * reference for a 16-bit wav (ssr_eval/metrics.py:22-23, ssr_eval/eval.py:133-134, 242).  Host-buffer callers
+ * upload the 2-byte samples and convert on the device: half the PCIe traffic, bit-identical values.
+ * ------------------------------------------------------------------------------------------ */
+int ssr_pcm16_to_float(const int16_t* src_dev, float* dst_dev, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

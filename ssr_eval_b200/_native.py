@@ -62,6 +62,7 @@ def lib():
     L.ssr_sosfiltfilt_workspace_bytes.argtypes = [vp, c_int, c_int]
     L.ssr_sosfiltfilt_workspace_bytes.restype = c_sz
     L.ssr_sosfiltfilt_batched.argtypes = [vp, c_int, vp, c_int, vp, vp, vp, c_int, vp, vp, c_sz, vp]
+    L.ssr_pcm16_to_float.argtypes = [vp, vp, c_i64, vp]
     _lib = L
     return L
 
@@ -97,4 +98,5 @@ EXPORTED_SYMBOLS = (
     "ssr_lowpass_plan_create", "ssr_lowpass_plan_destroy", "ssr_stft_hard_lowpass_batched",
     "ssr_splice_plan_create", "ssr_splice_plan_destroy", "ssr_stft_splice_istft_batched",
     "ssr_sosfiltfilt_workspace_bytes", "ssr_sosfiltfilt_batched",
+    "ssr_pcm16_to_float",
 )

@@ -1,0 +1,58 @@
+// pcm.cu -- K0: 16-bit PCM -> float32 on the device.
+//
+// The reference reads its wav files through librosa.load / soundfile (ssr_eval/metrics.py:22-23,
+// ssr_eval/eval.py:133-134, 242), which turn a 16-bit sample s into float32(s) / 32768.  VCTK (and every
+// file the reference writes with sf.write) is 16-bit PCM, so the host-buffer entry points upload the
+// 2-byte samples and convert here: half the PCIe bytes of a float32 upload, bit-identical values
+// (int16 -> float32 is exact and so is the scaling by 2^-15).
+// HBM-bound streaming kernel: 6 algorithmic bytes per sample (2 read + 4 written); a thread converts 8
+// samples (one 16-byte load, two 16-byte stores); grid = a multiple of the SM count, grid-stride loop.
+#include "common.cuh"
+
+namespace ssr {
+
+__global__ void __launch_bounds__(256) k_pcm16_to_f32(const int16_t* __restrict__ src, float* __restrict__ dst,
+                                                      long long n) {
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  constexpr float kScale = 1.0f / 32768.0f;
+  if (aligned) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+      const int4 v = __ldcs(reinterpret_cast<const int4*>(src) + i);  // streamed once: evict-first
+      const int w[4] = {v.x, v.y, v.z, v.w};
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[2 * j] = (float)(short)(w[j] & 0xffff) * kScale;
+        f[2 * j + 1] = (float)(short)(w[j] >> 16) * kScale;
+      }
+      float4* o = reinterpret_cast<float4*>(dst) + 2 * i;
+      o[0] = make_float4(f[0], f[1], f[2], f[3]);
+      o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      dst[i] = (float)src[i] * kScale;
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      dst[i] = (float)src[i] * kScale;
+  }
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+extern "C" int ssr_pcm16_to_float(const int16_t* src_dev, float* dst_dev, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!src_dev || !dst_dev))) return fail(SSR_ERR_INVALID, "ssr_pcm16_to_float: bad argument");
+  if (n == 0) return SSR_OK;
+  int dev = 0, sms = 0;
+  SSR_CUDA_TRY(cudaGetDevice(&dev));
+  SSR_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long want = ((n >> 3) + 255) / 256;
+  long long grid = (long long)sms * 8;  // 8 resident CTAs of 256 threads per SM
+  if (want < grid) grid = want < 1 ? 1 : want;
+  k_pcm16_to_f32<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src_dev, dst_dev, (long long)n);
+  SSR_LAUNCH_CHECK("k_pcm16_to_f32");
+  return SSR_OK;
+}

@@ -22,6 +22,9 @@ pytestmark = pytest.mark.gpu
 METRICS = ("lsd", "log_sispec", "sispec", "ssim")
 TOL = {"lsd": 1e-4, "log_sispec": 1e-4, "sispec": 2e-3, "ssim": 1e-3}
 TOL_EXACT = {"lsd": 2e-5, "log_sispec": 2e-5, "sispec": 2e-5}
+# L = 240000: at T*F = 4.8e5 elements the reference's own float32 torch.sum / torch.norm reductions move log_sispec /
+# sispec (DESIGN.md "Numerics"; distribution over 64 full-size pairs in profiles/r02_logsispec_distribution.md)
+LONG_TOL = {"lsd": 1e-4, "log_sispec": 5e-4, "sispec": 2e-3, "ssim": 1e-3}
 
 
 def _assert_metrics(got, want, ctx="", tol=TOL):
@@ -187,7 +190,7 @@ def test_full_size_pairs_properties(engines):
     got = eng.metrics(est, tgt)
     # at T*F = 4.8e5 elements the reference's float32 reductions move log_sispec / sispec by up to ~5e-4
     # (DESIGN.md "Numerics"); the tight statement is the float64-reduction check below
-    long_tol = {"lsd": 1e-4, "log_sispec": 5e-4, "sispec": 2e-3, "ssim": 1e-3}
+    long_tol = LONG_TOL
     for i in (0, 1):
         _assert_metrics(dict(zip(METRICS, got[i])), oracle.evaluation(est[i], tgt[i], n_fft=2048, hop=512),
                         f"full {i}", long_tol)
@@ -198,6 +201,59 @@ def test_full_size_pairs_properties(engines):
     assert abs(got[3][0]) < 1e-6, got[3]
     again = eng.metrics(est[::-1], tgt[::-1])[::-1]
     assert np.array_equal(again, got)
+
+
+def test_full_size_pairs_at_the_reference_48k_setting(engines):
+    """L = 240000 at n_fft 2229 / hop 480 -- what AudioMetrics(48000) runs (metrics.py:16-19) and what the
+    ``extras`` lines of bench.py time: all four metrics of a hard-low-passed and a benign pair against the oracle,
+    the PFA kernel against the generic Bluestein path being covered by test_specialised_and_generic_k1_kernels_agree."""
+    eng = engines(2229, 480)
+    L = 240000
+    tgt = [speech_like(L, sr=48000, seed=710 + i) for i in range(3)]
+    est = [oracle.lowpass(tgt[0], 12000, 48000, order=1, _type="stft_hard").astype(np.float32),
+           (tgt[1] + 1e-3 * np.random.default_rng(8).standard_normal(L)).astype(np.float32),
+           (0.5 * tgt[2]).astype(np.float32)]
+    got = eng.metrics(est, tgt)
+    for i in (0, 1):
+        _assert_metrics(dict(zip(METRICS, got[i])), oracle.evaluation(est[i], tgt[i], n_fft=2229, hop=480),
+                        f"full-size 2229 pair {i}", LONG_TOL)
+        _assert_metrics(dict(zip(METRICS, got[i])), oracle.evaluation_exact_reductions(est[i], tgt[i], 2229, 480),
+                        f"full-size 2229 pair {i} exact", TOL_EXACT)
+    assert abs(got[2][0] - np.log10(4.0)) < 1e-4, got[2]
+    again = eng.metrics(est[::-1], tgt[::-1])[::-1]
+    assert np.array_equal(again, got)
+
+
+def test_pcm16_upload_path_is_bit_identical_to_float_upload(engines):
+    """K0 + HostPipeline: int16 PCM host buffers (what a 16-bit wav holds) uploaded as 2-byte samples and
+    converted on the device give bit-identical metrics to uploading float32(s) / 32768 (librosa.load's values)."""
+    from ssr_eval_b200.engine import HostPipeline, pcm16_to_float_device, offsets_of
+    rng = np.random.default_rng(11)
+    for n in (1, 7, 8, 4097, 100003):  # tails and (via the slice offset) unaligned pointers
+        raw = rng.integers(-32768, 32768, size=n + 3, dtype=np.int16)
+        raw[:2] = (-32768, 32767)
+        for o in (0, 1, 3):
+            got = pcm16_to_float_device(torch.from_numpy(raw).cuda()[o:o + n]).cpu().numpy()
+            assert np.array_equal(got, raw[o:o + n].astype(np.float32) / 32768.0), (n, o)
+    lens = [24000, 5000, 31337, 2048]
+    tgt = [np.round(speech_like(n, 48000, seed=900 + i) * 32768).clip(-32768, 32767).astype(np.int16)
+           for i, n in enumerate(lens)]
+    est = [np.round((t / 32768.0 * 0.7 + 1e-3 * rng.standard_normal(len(t))) * 32768).clip(-32768, 32767).astype(np.int16)
+           for t in tgt]
+    off = offsets_of(lens)
+    eng = engines(2048, 512)
+    pipe = HostPipeline(eng, len(lens), max(lens), chunk_pairs=2)
+    e16 = torch.from_numpy(np.concatenate(est)).pin_memory()
+    t16 = torch.from_numpy(np.concatenate(tgt)).pin_memory()
+    e32 = (e16.float() / 32768.0).pin_memory()
+    t32 = (t16.float() / 32768.0).pin_memory()
+    a = pipe.run(e16, t16, off)
+    b = pipe.run(e32, t32, off)
+    c = pipe.run(e32, t16, off)   # mixed: float32 estimate (a model output in memory), PCM16 target (a wav file)
+    d = eng.metrics([x.astype(np.float32) / 32768.0 for x in est], [x.astype(np.float32) / 32768.0 for x in tgt])
+    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)
+    with pytest.raises(TypeError):
+        pipe.run(e32.double(), t32, off)
 
 
 @pytest.mark.parametrize("up,down", [(160, 147), (147, 160), (441, 160), (80, 147), (3, 1), (1, 2)])
@@ -442,7 +498,7 @@ def _helper_reference_runs():
     return json.load(open(path))
 
 
-@pytest.mark.parametrize("run_name", ["identity_all_settings", "upsampling_testee_output_48k"])
+@pytest.mark.parametrize("run_name", ["identity_all_settings", "upsampling_testee_output_48k", "reference_test_py"])
 def test_helper_against_the_reference_orchestrator(tmp_path, monkeypatch, run_name):
     """SSR_Eval_Helper.evaluate() against tests/golden/helper_reference_runs.json, the result of the REFERENCE'S
     OWN SSR_Eval_Helper.evaluate() (tests/golden/make_golden_helper.py) on the same synthetic data set: same
