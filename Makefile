@@ -24,7 +24,16 @@ build/host_emul: tests/host_emul.cu $(SRC)/fft_core.cuh $(SRC)/stft_tables.hpp $
 	@mkdir -p build
 	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -o $@ $<
 
+# A/B variants (development): make variant VARIANT=name VARIANT_FLAGS="-DSSR_..." -> build/variants/libssr_b200_name.so
+# (timed against the in-tree build by tools/ab_lib.py in one process)
+VARIANT ?= x
+variant:
+	@mkdir -p build/variants/obj_$(VARIANT)
+	@for f in $(SRCS); do b=$$(basename $$f .cu); \
+	  $(NVCC) $(NVFLAGS) $(VARIANT_FLAGS) -c $$f -o build/variants/obj_$(VARIANT)/$$b.o & done; wait
+	$(NVCC) -shared $(ARCH) -o build/variants/libssr_b200_$(VARIANT).so build/variants/obj_$(VARIANT)/*.o -cudart static
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean
+.PHONY: all clean variant

@@ -75,13 +75,22 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
   tmem_wait_st();
   if (tid < 120) tw2[tid] = P.tw[16 * (tid & 7) * ((tid >> 3) + 1)];  // tw2[(q-1)*8 + j] = W_128^{jq}
   int ia, ib;
+#ifdef SSR_WARPLOCAL
+  // passes 2 and 3 of a sub-transform block AND of its Hermitian-partner block run in one warp (k1_map.cuh):
+  // the second exchange is warp-local
+  bool special;
+  v2w_thread_butterflies(tid, &ia, &ib, &special);
+  const int blk2 = v2w_pass2_block(tid);
+#else
   v2_thread_butterflies(tid, &ia, &ib);
   const bool special = (tid == kV2Threads - 1);
+  const int blk2 = tid >> 3;
+#endif
   const int ka = v2_klow(ia), kb = v2_klow(ib);
   const int j2 = tid & 7;
   // padded slots: pass 1 element q -> p1 + 144 q; pass 2 element r -> p2 + 9 r; pass 3 -> 9 i + r
   cd* const b1 = buf + pad_idx(tid);
-  cd* const b2 = buf + pad_idx((tid >> 3) * 128 + j2);
+  cd* const b2 = buf + pad_idx(blk2 * 128 + j2);
   const cd* const b3a = buf + 9 * ia;
   const cd* const b3b = buf + 9 * ib;
   const cd* const t2 = tw2 + j2;
@@ -228,7 +237,11 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       b2[0] = v[0];
 #pragma unroll
       for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
+#ifdef SSR_WARPLOCAL
+      __syncwarp();
+#else
       __syncthreads();
+#endif
       // ---- pass 3: two radix-8 butterflies (a and its Hermitian partner b), no twiddles
       cd* a = v;
       cd* b = v + 8;

@@ -211,12 +211,23 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
   for (int q = 1; q < 16; ++q) tw1[q - 1] = P.tw[tid * q];
   if (tid < 120) tw2[tid] = P.tw[16 * (tid & 7) * ((tid >> 3) + 1)];
   int ia, ib;
+#ifdef SSR_WARPLOCAL
+  // passes 2 / 3 (and inverse passes 1 / 2) of a sub-transform block and of its Hermitian-partner block run in one
+  // warp (k1_map.cuh): those two exchanges are warp-local, __syncwarp() instead of a CTA barrier
+  bool special;
+  v2w_thread_butterflies(tid, &ia, &ib, &special);
+  const int blk2 = v2w_pass2_block(tid);
+#define SSR_SYNC_LOCAL() __syncwarp()
+#else
   v2_thread_butterflies(tid, &ia, &ib);
   const bool special = (tid == kV2Threads - 1);
+  const int blk2 = tid >> 3;
+#define SSR_SYNC_LOCAL() __syncthreads()
+#endif
   const int ka = v2_klow(ia), kb = v2_klow(ib);
   const int j2 = tid & 7;
   cf* const b1 = buf + pad16(tid);                      // element tid + 128 q -> b1[136 q]
-  cf* const b2 = buf + pad16((tid >> 3) * 128 + j2);    // element base + 8 r   -> b2[8 r + r/2]
+  cf* const b2 = buf + pad16(blk2 * 128 + j2);          // element base + 8 r   -> b2[8 r + r/2]
   cf* const b3a = buf + 8 * ia + (ia >> 1);             // element 8 i + r      -> b3[r]
   cf* const b3b = buf + 8 * ib + (ib >> 1);
   const cf* const t2 = tw2 + j2;
@@ -291,7 +302,7 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
     b2[0] = v[0];
 #pragma unroll
     for (int q = 1; q < 16; ++q) b2[8 * q + (q >> 1)] = cmul(v[q], t2[(q - 1) * 8]);
-    __syncthreads();
+    SSR_SYNC_LOCAL();
     // ---- forward pass 3 (registers), bin processing, inverse pass 1 (registers)
     cf* a = v;
     cf* b = v + 8;
@@ -339,7 +350,7 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
       b3a[r] = a[r];
       b3b[r] = b[r];
     }
-    __syncthreads();
+    SSR_SYNC_LOCAL();
     // ---- inverse pass 2
     v[0] = b2[0];
 #pragma unroll

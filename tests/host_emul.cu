@@ -191,7 +191,47 @@ static int check_v2() {
   for (int k = 0; k <= N / 2; ++k)
     if (seen[k] != 1) ++bad;
   printf("v2 (16x16x8) map: bins covered once: %s, maxerr %.3e\n", bad ? "NO" : "yes", maxerr);
-  return (bad == 0 && maxerr < 1e-10) ? 0 : 1;
+  // warp-local variant: same coverage, and every element a warp reads in pass 3 was written by that warp in pass 2
+  std::vector<int> seen2(N / 2 + 1, 0), owner(N, -1);
+  int bad2 = 0;
+  double maxerr2 = 0;
+  for (int t = 0; t < 128; ++t) {  // pass-2 butterfly of thread t writes elements 128 blk + j2 + 8 r
+    const int blk = v2w_pass2_block(t), j2 = t & 7;
+    for (int r = 0; r < 16; ++r) {
+      if (owner[128 * blk + j2 + 8 * r] != -1) ++bad2;
+      owner[128 * blk + j2 + 8 * r] = t >> 5;
+    }
+  }
+  auto emit2 = [&](int k, cd zk, cd znk) {
+    if (k < 0 || k > N / 2) { ++bad2; return; }
+    seen2[k]++;
+    int nk = (N - k) % N;
+    maxerr2 = fmax(maxerr2, fmax(fabs(zk.x - (double)Xr[k]), fabs(zk.y - (double)Xi[k])));
+    maxerr2 = fmax(maxerr2, fmax(fabs(znk.x - (double)Xr[nk]), fabs(znk.y - (double)Xi[nk])));
+  };
+  for (int t = 0; t < 128; ++t) {
+    int ia, ib;
+    bool special;
+    v2w_thread_butterflies(t, &ia, &ib, &special);
+    cd a[8], b[8];
+    for (int r = 0; r < 8; ++r) {
+      if (owner[8 * ia + r] != (t >> 5) || owner[8 * ib + r] != (t >> 5)) ++bad2;
+      a[r] = buf[pad_idx(8 * ia + r)];
+      b[r] = buf[pad_idx(8 * ib + r)];
+    }
+    bfly8<false>(a);
+    bfly8<false>(b);
+    const int ka = v2_klow(ia), kb = v2_klow(ib);
+    for (int q = 0; q < 4; ++q) {
+      emit2(ka + 256 * q, a[q], special ? a[(8 - q) & 7] : b[7 - q]);
+      emit2(kb + 256 * q, b[q], special ? b[7 - q] : a[7 - q]);
+    }
+    if (special) emit2(1024, a[4], a[4]);
+  }
+  for (int k = 0; k <= N / 2; ++k)
+    if (seen2[k] != 1) ++bad2;
+  printf("v2 warp-local map: bins covered once + pass 2 -> 3 stays in the warp: %s, maxerr %.3e\n", bad2 ? "NO" : "yes", maxerr2);
+  return (bad == 0 && maxerr < 1e-10 && bad2 == 0 && maxerr2 < 1e-10) ? 0 : 1;
 }
 
 

@@ -22,6 +22,7 @@ ap.add_argument("--nfft", type=int, default=2048)
 ap.add_argument("--hop", type=int, default=512)
 ap.add_argument("--flags", default="1,7,15")
 ap.add_argument("--pairs", type=int, default=1024)
+ap.add_argument("--k4", action="store_true", help="also time K4 (stft_hard 2048/441, 1024 x 220500) and K3 (160/147)")
 ap.add_argument("libs", nargs="+")
 a = ap.parse_args()
 default_path = N._LIB_PATH
@@ -53,3 +54,27 @@ for lib in a.libs:
                           "ms": round(ms, 4), "pairs_per_s": round(n / ms * 1e3, 1),
                           "mean": [float(x) for x in out.nanmean(dim=0).cpu()]}), flush=True)
     del eng
+    if a.k4:
+        L4 = 220500
+        x4 = tg[:n * L4]
+        off4 = engine.offsets_of([L4] * n)
+        off4_d = torch.from_numpy(off4).to(dev)
+        lp = engine.HardLowpass(2048, 441)
+        cuts = [lp.cut_bin(12000 / 22050)] * n
+        rs = engine.PolyphaseResampler(160, 147)
+        for name, fn in (("k4", lambda: lp.apply_device(x4, off4, cuts, off4_d)),
+                         ("k3_160_147", lambda: rs.resample_device(x4, off4, off4_d)[0])):
+            for _ in range(2):
+                y4 = fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                y4 = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print(json.dumps({"lib": os.path.basename(N._LIB_PATH), "kernel": name, "ms": round(ms, 4),
+                              "utt_per_s": round(n / ms * 1e3, 1), "checksum": float(y4.double().abs().sum().cpu()),
+                              "sum": float(y4.double().sum().cpu())}), flush=True)
+        del lp, rs, y4
