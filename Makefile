@@ -1,13 +1,13 @@
 # Builds the C-ABI shared library (hand-written sm_100a CUDA) in-tree.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas --expt-relaxed-constexpr
+NVFLAGS := -DSSR_WARPLOCAL -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas --expt-relaxed-constexpr
 SRC := ssr_eval_b200/csrc
 OBJ := build/obj
 LIB := ssr_eval_b200/lib/libssr_b200.so
-SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu $(SRC)/stft_splice.cu $(SRC)/sosfiltfilt.cu $(SRC)/pcm.cu
+SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu $(SRC)/stft_splice.cu $(SRC)/sosfiltfilt.cu $(SRC)/pcm.cu $(SRC)/stft_lowpass_dense.cu
 OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(SRCS))
-HDRS := $(wildcard $(SRC)/*.cuh) $(SRC)/stft_tables.hpp include/ssr_b200.h
+HDRS := $(wildcard $(SRC)/*.cuh) $(SRC)/stft_tables.hpp include/ssr_b200.h Makefile
 
 all: $(LIB)
 

@@ -307,6 +307,7 @@ def run_gpu(args):
     ms = float(t.item())
     value = world * n_pairs * args.steps / (ms * 1e-3)
     lsd_mean = float(out[:, 0].mean().item())
+    timed_first = out[:2].cpu().numpy()  # values of the timed launches (out is reused by the context runs below)
 
     # ---- end to end through the public host API: pinned host buffers -> H2D -> kernels -> D2H.
     # Headline e2e: the host batch is 16-bit PCM -- the sample format of the wav files the reference reads
@@ -378,13 +379,14 @@ def run_gpu(args):
         # oracle -- the checker, outside every timed region -- against the values the timed kernels produced
         import oracle
         got_all = eng.metrics_device(est[:2 * LENGTH], tgt[:2 * LENGTH], off[:3], N.METRIC_ALL).cpu().numpy()
-        timed = out[:2].cpu().numpy()
+        timed = timed_first
         diffs = {m: 0.0 for m in N.METRIC_NAMES}
         for i in range(2):
             e_i = est[i * LENGTH:(i + 1) * LENGTH].cpu().numpy()
             t_i = tgt[i * LENGTH:(i + 1) * LENGTH].cpu().numpy()
             want = oracle.evaluation(e_i, t_i, n_fft=N_FFT, hop=HOP)
-            assert got_all[i, 0] == timed[i, 0], "LSD of the timed launch and of the all-metrics launch differ"
+            # (another batch size groups the frames into other work items: float64 partial sums regrouped, ~1e-13)
+            assert abs(got_all[i, 0] - timed[i, 0]) < 1e-9, "LSD of the timed launch and of the all-metrics launch differ"
             for j, m in enumerate(N.METRIC_NAMES):
                 diffs[m] = max(diffs[m], abs(float(got_all[i, j]) - float(want[m])))
         check["oracle_pairs"] = 2

@@ -143,6 +143,27 @@ int ssr_stft_hard_lowpass_batched(const ssr_lowpass_plan* plan, const float* x_d
                                   const int32_t* cut_bins_dev, float* y_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K4d: reference-faithful ("dense") mode of the STFT hard low-pass.  torchlibrosa's STFT / ISTFT
+ * (ssr_eval/dsp.py:21-39, used by ssr_eval/lowpass.py:17-28) are not FFTs but dense float32 convolutions with
+ * (DFT matrix x Hann) kernels; the bins above the cutoff of the result ARE the rounding noise of that arithmetic and
+ * LSD / log-sispec of such an estimate measure it.  This mode multiplies by the same float32 matrices (built on the
+ * host with torchlibrosa's formula: stft_w_* = (n_fft/2+1) x n_fft, istft_w_* = n_fft x n_fft (out, in),
+ * ola_window = window^2) in the accumulation order of the reference's convolutions (see stft_lowpass_dense.cu), with
+ * IEEE sqrt / division: bit-identical to the CPU reference for almost every sample, ~100x the arithmetic of K4.
+ * Utterances must be longer than n_fft/2 (torchlibrosa's reflect padding).  Any workspace that holds the longest
+ * utterance works (the batch is chunked); ssr_stft_hard_lowpass_dense_workspace_bytes = one chunk for everything.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssr_lowpass_dense_plan ssr_lowpass_dense_plan;
+int ssr_lowpass_dense_plan_create(ssr_lowpass_dense_plan** plan, int n_fft, int hop, const float* stft_w_real_host,
+                                  const float* stft_w_imag_host, const float* istft_w_real_host,
+                                  const float* istft_w_imag_host, const float* ola_window_host);
+int ssr_lowpass_dense_plan_destroy(ssr_lowpass_dense_plan* plan);
+size_t ssr_stft_hard_lowpass_dense_workspace_bytes(const ssr_lowpass_dense_plan* plan, const int64_t* offsets_host, int n);
+int ssr_stft_hard_lowpass_dense_batched(const ssr_lowpass_dense_plan* plan, const float* x_dev, const int64_t* offsets_host,
+                                        const int64_t* offsets_dev, int n, const int32_t* cut_bins_dev, float* y_dev,
+                                        void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K6 ("next" row): the STFT splice of BasicTestee.postprocessing
  * (ssr_eval/eval.py:33-41): librosa.stft (n_fft 2048, hop 512) of the model input x and of the model
  * output, bins below cut_bin taken from x, librosa.istft(length = len(out)).  x and out of a pair

@@ -63,6 +63,11 @@ def lib():
     L.ssr_sosfiltfilt_workspace_bytes.restype = c_sz
     L.ssr_sosfiltfilt_batched.argtypes = [vp, c_int, vp, c_int, vp, vp, vp, c_int, vp, vp, c_sz, vp]
     L.ssr_pcm16_to_float.argtypes = [vp, vp, c_i64, vp]
+    L.ssr_lowpass_dense_plan_create.argtypes = [ctypes.POINTER(vp), c_int, c_int, vp, vp, vp, vp, vp]
+    L.ssr_lowpass_dense_plan_destroy.argtypes = [vp]
+    L.ssr_stft_hard_lowpass_dense_workspace_bytes.argtypes = [vp, vp, c_int]
+    L.ssr_stft_hard_lowpass_dense_workspace_bytes.restype = c_sz
+    L.ssr_stft_hard_lowpass_dense_batched.argtypes = [vp, vp, vp, vp, c_int, vp, vp, vp, c_sz, vp]
     _lib = L
     return L
 
@@ -99,4 +104,6 @@ EXPORTED_SYMBOLS = (
     "ssr_splice_plan_create", "ssr_splice_plan_destroy", "ssr_stft_splice_istft_batched",
     "ssr_sosfiltfilt_workspace_bytes", "ssr_sosfiltfilt_batched",
     "ssr_pcm16_to_float",
+    "ssr_lowpass_dense_plan_create", "ssr_lowpass_dense_plan_destroy",
+    "ssr_stft_hard_lowpass_dense_workspace_bytes", "ssr_stft_hard_lowpass_dense_batched",
 )

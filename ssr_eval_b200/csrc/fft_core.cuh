@@ -161,6 +161,27 @@ SSR_HD void bfly16(C2<T>* x) {
     }
 }
 
+// The same 16-point DFT in two steps, for callers that interleave the second radix-4 stage with other work (the
+// twiddle prefetch of K1's pass 2): after bfly16_first, bfly16_group<q0> leaves y[q0 + 4 q1] in x[4 q0 + q1].
+template <bool INV, typename T>
+SSR_HD void bfly16_first(C2<T>* x) {
+#pragma unroll
+  for (int r0 = 0; r0 < 4; ++r0) bfly4<INV>(x[r0], x[4 + r0], x[8 + r0], x[12 + r0]);
+  x[5] = mul_w16<INV, 1>(x[5]);
+  x[6] = mul_w16<INV, 2>(x[6]);
+  x[7] = mul_w16<INV, 3>(x[7]);
+  x[9] = mul_w16<INV, 2>(x[9]);
+  x[10] = mul_mi<INV>(x[10]);
+  x[11] = mul_w16<INV, 6>(x[11]);
+  x[13] = mul_w16<INV, 3>(x[13]);
+  x[14] = mul_w16<INV, 6>(x[14]);
+  x[15] = mul_w16<INV, 9>(x[15]);
+}
+template <bool INV, int Q0, typename T>
+SSR_HD void bfly16_group(C2<T>* x) {
+  bfly4<INV>(x[4 * Q0], x[4 * Q0 + 1], x[4 * Q0 + 2], x[4 * Q0 + 3]);
+}
+
 template <int R, bool INV, typename T>
 SSR_HD void bfly(C2<T>* x) {
   if (R == 16) {

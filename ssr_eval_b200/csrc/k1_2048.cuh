@@ -3,8 +3,21 @@
 #include "k1_common.cuh"
 #include "k1_map.cuh"
 #include "tmem.cuh"
+#include <type_traits>
 
 namespace ssr {
+
+// loads the compiler may not sink towards their use (issued where they are written)
+__device__ __forceinline__ double ldg_f64_pinned(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ cd lds_cd(const cd* p) {
+  cd r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------------
 // K1, specialised: n_fft = 2048 (BASELINE config 2 and every evaluation at 44.1 kHz).
@@ -128,12 +141,24 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
           // chunk (f + 2 + r / 4) mod 4 (4 blocks x (target, est) x float64 = 16 columns per chunk)
           const unsigned ring = tmem_base + 64;
           const int c0 = (int)((f + 2) & 3);
+          // the 16 half-window values are requested first (L1 hits, but ~40+ cycles): issued behind the tensor-memory
+          // traffic they left the FP64 multiplies below waiting on the long scoreboard (ncu: ~3 % of all warp time)
+#ifndef SSR_K1_WIN_AHEAD
+#define SSR_K1_WIN_AHEAD 8
+#endif
+          constexpr int kWinAhead = SSR_K1_WIN_AHEAD;  // window values requested ahead of the tensor-memory wait
           if (ring_next == f) {
             tmem_wait_st();  // the previous frame's ring stores
             unsigned r0[16], r1[16], r2[16], r3[16];
             tmem_ld16(ring + 16 * ((c0 + 0) & 3), r0);
             tmem_ld16(ring + 16 * ((c0 + 1) & 3), r1);
             tmem_ld16(ring + 16 * ((c0 + 2) & 3), r2);
+            // the first half-window values are requested now (L1 hits, but ~40+ cycles): all 16 issued behind the
+            // tensor-memory traffic left the FP64 multiplies below waiting on the long scoreboard (ncu: ~3 % of all
+            // warp time); the register file does not hold all 16 next to the three TMEM chunks
+            double wv[kWinAhead > 0 ? kWinAhead : 1];
+#pragma unroll
+            for (int r = 0; r < kWinAhead; ++r) wv[r] = ldg_f64_pinned(P.win_half + tid + 128 * r);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               v[12 + i] = cd{(double)pre_t[i], (double)pre_e[i]};
@@ -145,6 +170,11 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
             tmem_unpack4(r0, v);
             tmem_unpack4(r1, v + 4);
             tmem_unpack4(r2, v + 8);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const double w = r < kWinAhead ? wv[r] : __ldg(P.win_half + tid + 128 * r);
+              v[r] = cd{w * v[r].x, w * v[r].y};
+            }
           } else {
 #pragma unroll
             for (int r = 0; r < 16; ++r) v[r] = cd{(double)__ldg(pt + 128 * r), (double)__ldg(pe + 128 * r)};
@@ -154,13 +184,13 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
               tmem_pack4(v + 4 * k, rr);
               tmem_st16(ring + 16 * ((c0 + k) & 3), rr);
             }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const double w = __ldg(P.win_half + tid + 128 * r);
+              v[r] = cd{w * v[r].x, w * v[r].y};
+            }
           }
           ring_next = f + 1;
-#pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            const double w = __ldg(P.win_half + tid + 128 * r);
-            v[r] = cd{w * v[r].x, w * v[r].y};
-          }
         } else {
 #pragma unroll
           for (int r = 0; r < 16; ++r) {
@@ -233,10 +263,43 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       // ---- pass 2: sub-transforms of length 128 (stride 8)
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[r] = b2[9 * r];
+#ifdef SSR_K1_PASS2_SERIAL
       bfly16<false>(v);
       b2[0] = v[0];
 #pragma unroll
       for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
+#else
+      // The last radix-4 stage is done group by group (outputs q0, q0+4, q0+8, q0+12), and the 4 twiddles of the NEXT
+      // group are fetched from shared memory before the current group is computed, multiplied and stored: the
+      // straightforward form (load twiddle -> multiply -> store, 15 times) serialised 12 shared-memory latencies
+      // at the end of the pass with nothing else to issue (ncu: ~19 % of all warp time, short scoreboard).
+      bfly16_first<false>(v);
+      {
+        cd w[2][4];
+        auto fetch = [&](int q0, cd* dst) {
+#pragma unroll
+          for (int q1 = 0; q1 < 4; ++q1) {
+            const int q = q0 + 4 * q1;
+            if (q > 0) dst[q1] = lds_cd(t2 + (q - 1) * 8);
+          }
+        };
+        fetch(0, w[0]);
+        auto group = [&](auto q0c) {
+          constexpr int q0 = decltype(q0c)::value;
+          if (q0 < 3) fetch(q0 + 1, w[(q0 + 1) & 1]);
+          bfly16_group<false, q0>(v);
+#pragma unroll
+          for (int q1 = 0; q1 < 4; ++q1) {
+            const int q = q0 + 4 * q1;
+            b2[9 * q] = q > 0 ? cmul(v[4 * q0 + q1], w[q0 & 1][q1]) : v[0];
+          }
+        };
+        group(std::integral_constant<int, 0>{});
+        group(std::integral_constant<int, 1>{});
+        group(std::integral_constant<int, 2>{});
+        group(std::integral_constant<int, 3>{});
+      }
+#endif
 #ifdef SSR_WARPLOCAL
       __syncwarp();
 #else

@@ -298,6 +298,81 @@ class HardLowpass:
         return [y[s:e].copy() for s, e in zip(off[:-1], off[1:])]
 
 
+def torchlibrosa_dft_matrices(n_fft):
+    """The float32 convolution kernels torchlibrosa's ``STFT`` / ``ISTFT`` modules build (the classes behind
+    ssr_eval/dsp.py:21-39), restated from torchlibrosa/stft.py (``DFTBase.dft_matrix`` / ``idft_matrix``,
+    ``STFT.__init__``, ``ISTFT.init_real_imag_conv`` / ``init_overlap_add_window``; 0.0.7-0.0.9):
+        W  = np.power(exp(-2j*pi/n), x*y)               Wi = np.power(exp(+2j*pi/n), x*y) / n
+        stft  conv_real / conv_imag = real / imag (W[:, :n/2+1] * hann[:, None]).T          -> (n/2+1, n)
+        istft conv_real / conv_imag = real / imag (Wi * hann[None, :]).T                     -> (n, n) (out, in)
+        ola_window = hann ** 2
+    with the periodic Hann window, evaluated in float64 (complex128 ``np.power``) and cast to float32 as there.
+    Returns (stft_w_real, stft_w_imag, istft_w_real, istft_w_imag, ola_window), C-contiguous float32."""
+    n = int(n_fft)
+    hann = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)  # scipy.signal.get_window("hann", n, fftbins=True)
+    x, y = np.meshgrid(np.arange(n), np.arange(n))
+    W = np.power(np.exp(-2 * np.pi * 1j / n), x * y)
+    Wi = np.power(np.exp(2 * np.pi * 1j / n), x * y) / n
+    F = n // 2 + 1
+    c = np.ascontiguousarray
+    fw = W[:, :F] * hann[:, None]
+    iw = Wi * hann[None, :]
+    return (c(np.real(fw).T, dtype=np.float32), c(np.imag(fw).T, dtype=np.float32),
+            c(np.real(iw).T, dtype=np.float32), c(np.imag(iw).T, dtype=np.float32), c(hann ** 2, dtype=np.float32))
+
+
+class HardLowpassDense:
+    """K4d: stft_hard_lowpass_v0 in the reference's own arithmetic -- dense float32 DFT / IDFT products in the
+    accumulation order of torch's CPU convolutions (csrc/stft_lowpass_dense.cu).  ~100x the arithmetic of
+    ``HardLowpass``; use it when the noise floor above the cutoff has to be the reference's (LSD / log-sispec of an
+    unprocessed ``proc_fft_*`` input)."""
+
+    WORKSPACE_BYTES = 3 << 30  # per launch sequence; the batch is chunked to fit
+
+    def __init__(self, n_fft=2048, hop=441):
+        _require_cuda()
+        self.n_fft, self.hop = int(n_fft), int(hop)
+        self.n_bins = self.n_fft // 2 + 1
+        self._plan = ctypes.c_void_p()
+        mats = torchlibrosa_dft_matrices(self.n_fft)
+        N.check(N.lib().ssr_lowpass_dense_plan_create(ctypes.byref(self._plan), self.n_fft, self.hop,
+                                                      *[_np_ptr(m) for m in mats]), "ssr_lowpass_dense_plan_create")
+        self._ws = _Workspace()
+
+    def __del__(self):
+        try:
+            if self._plan:
+                N.lib().ssr_lowpass_dense_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+    def cut_bin(self, lowpass_ratio):
+        return int(self.n_bins * lowpass_ratio)  # lowpass.py:23
+
+    def apply_device(self, x_dev, offsets, cut_bins, offsets_dev=None):
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        if offsets_dev is None:
+            offsets_dev = torch.from_numpy(off).to(x_dev.device)
+        n = len(off) - 1
+        cb = torch.as_tensor(np.asarray(cut_bins, dtype=np.int32)).to(x_dev.device)
+        assert cb.numel() == n and x_dev.dtype == torch.float32
+        y = torch.empty(int(off[-1]), dtype=torch.float32, device=x_dev.device)
+        need = N.lib().ssr_stft_hard_lowpass_dense_workspace_bytes(self._plan, _np_ptr(off), n)
+        longest = N.lib().ssr_stft_hard_lowpass_dense_workspace_bytes(
+            self._plan, _np_ptr(np.array([0, int(np.diff(off).max())], dtype=np.int64)), 1)
+        ws = self._ws.get(max(min(need, self.WORKSPACE_BYTES), longest + 8 * (n + 64)), x_dev.device)
+        N.check(N.lib().ssr_stft_hard_lowpass_dense_batched(self._plan, _ptr(x_dev), _np_ptr(off), _ptr(offsets_dev), n,
+                                                            _ptr(cb), _ptr(y), _ptr(ws), ws.numel(), _stream()),
+                "ssr_stft_hard_lowpass_dense_batched")
+        return y
+
+    def apply(self, wav_list, lowpass_ratios):
+        x_h, off = pack_ragged(wav_list, pinned=True)
+        cuts = [self.cut_bin(r) for r in lowpass_ratios]
+        y = self.apply_device(x_h.cuda(non_blocking=True), off, cuts).cpu().numpy()
+        return [y[s:e].copy() for s, e in zip(off[:-1], off[1:])]
+
+
 class SpliceIstft:
     """K6: the STFT splice + ISTFT of BasicTestee.postprocessing (ssr_eval/eval.py:28-41)."""
 

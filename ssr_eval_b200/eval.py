@@ -67,6 +67,10 @@ class SSR_Eval_Helper:
     # resampler used when a file's native rate differs from input_sr / evaluation_sr ("polyphase" | "kaiser_best");
     # the reference leaves this to librosa.load (kaiser_best in 0.9) and to the sox binary -- see INTEGRATION.md
     load_res_type = "polyphase"
+    # arithmetic of the setting_fft degradation: None = lowpass.STFT_HARD_MODE ("fft" unless SSR_STFT_HARD_MODE says
+    # otherwise), "fft" = K4 (float32 FFT, fast), "dense" = K4d (the reference's dense float32 DFT arithmetic: the noise
+    # floor above the cutoff -- and with it LSD / log-sispec of an unprocessed proc_fft_* input -- is the reference's)
+    stft_hard_mode = None
 
     def __init__(self, testee, input_sr, output_sr, evaluation_sr=44100, test_name="test",
                  test_data_root="./datasets/vctk_test", setting_lowpass_filtering=None,
@@ -139,7 +143,7 @@ class SSR_Eval_Helper:
                 ratios.append((low_rate // 2) / int(sr / 2))
             waves = [x for x in xs for _ in keys]
             rr = [r for _ in xs for r in ratios]
-            ys = stft_hard_lowpass_batch(waves, rr)
+            ys = stft_hard_lowpass_batch(waves, rr, mode=self.stft_hard_mode)
             for i, o in enumerate(outs):
                 for j, key in enumerate(keys):
                     o[key] = ys[i * len(keys) + j]
@@ -158,6 +162,7 @@ class SSR_Eval_Helper:
         probe.setting_subsampling = self.setting_subsampling if subsampling else None
         probe.setting_fft = self.setting_fft if fft else None
         probe.setting_mp3_compression = None
+        probe.stft_hard_mode = self.stft_hard_mode
         return probe._degrade_batch([np.asarray(x)], sr)[0]
 
     def lowpass_butterworth(self, file, x, sr):

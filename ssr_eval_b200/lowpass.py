@@ -6,16 +6,29 @@ bessel: scipy designs the second-order sections on the host exactly as the refer
 import numpy as np
 from scipy.signal import butter, cheby1, cheby2, ellip, bessel
 
-from .engine import HardLowpass, PolyphaseResampler, sosfiltfilt_batch
+import os
+
+from .engine import HardLowpass, HardLowpassDense, PolyphaseResampler, sosfiltfilt_batch
 
 _hard = {}
 _resamplers = {}
 
+# Arithmetic of ``stft_hard``: "fft" (default) = K4, a float32 FFT -- the same algorithm to 2e-5 per sample, ~100x
+# faster, but a LOWER rounding-noise floor above the cutoff than the reference's dense float32 DFT products, which
+# moves LSD / log-sispec of an unprocessed proc_fft_* input by ~+0.25 / -0.05; "dense" = K4d,
+# the reference's own arithmetic (bit-identical to torchlibrosa on an AVX-512 host for almost every sample).
+# Set here, per call (``mode=``), or through the environment variable SSR_STFT_HARD_MODE.
+STFT_HARD_MODE = os.environ.get("SSR_STFT_HARD_MODE", "fft")
 
-def _hard_lowpass(n_fft=2048, hop=441):
-    key = (n_fft, hop)
+
+def _hard_lowpass(n_fft=2048, hop=441, mode=None):
+    mode = STFT_HARD_MODE if mode is None else mode
+    if mode not in ("fft", "dense"):
+        raise ValueError("stft_hard mode must be 'fft' or 'dense', got %r" % (mode,))
+    key = (n_fft, hop, mode)
     if key not in _hard:
-        _hard[key] = HardLowpass(n_fft, hop)  # FDomainHelper defaults, ssr_eval/dsp.py:9-10
+        # FDomainHelper defaults, ssr_eval/dsp.py:9-10
+        _hard[key] = HardLowpass(n_fft, hop) if mode == "fft" else HardLowpassDense(n_fft, hop)
     return _hard[key]
 
 
@@ -26,15 +39,15 @@ def _resampler(up, down):
     return _resamplers[key]
 
 
-def stft_hard_lowpass_v0(data, lowpass_ratio):
+def stft_hard_lowpass_v0(data, lowpass_ratio, mode=None):
     """ssr_eval/lowpass.py:17-28 -> float32 numpy of the input length."""
     x = np.asarray(data, dtype=np.float32)
-    return _hard_lowpass().apply([x], [lowpass_ratio])[0]
+    return _hard_lowpass(mode=mode).apply([x], [lowpass_ratio])[0]
 
 
-def stft_hard_lowpass_batch(waves, lowpass_ratios):
-    """Batched form: one kernel launch for all (utterance, ratio) pairs."""
-    return _hard_lowpass().apply([np.asarray(w, dtype=np.float32) for w in waves], lowpass_ratios)
+def stft_hard_lowpass_batch(waves, lowpass_ratios, mode=None):
+    """Batched form: one kernel launch (sequence) for all (utterance, ratio) pairs."""
+    return _hard_lowpass(mode=mode).apply([np.asarray(w, dtype=np.float32) for w in waves], lowpass_ratios)
 
 
 def align_length(x, y):

@@ -169,7 +169,7 @@ def test_per_family_degradation_methods_keys_and_calls(tmp_path, monkeypatch):
         calls.append(("lowpass", len(waves), highcut, fs, order, _type))
         return [np.asarray(w) * 0.5 for w in waves]
 
-    def fake_hard(waves, ratios):
+    def fake_hard(waves, ratios, mode=None):
         calls.append(("stft_hard", len(waves), [round(r, 6) for r in ratios]))
         return [np.asarray(w) * 0.25 for w in waves]
 

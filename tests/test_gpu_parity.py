@@ -251,7 +251,10 @@ def test_pcm16_upload_path_is_bit_identical_to_float_upload(engines):
     b = pipe.run(e32, t32, off)
     c = pipe.run(e32, t16, off)   # mixed: float32 estimate (a model output in memory), PCM16 target (a wav file)
     d = eng.metrics([x.astype(np.float32) / 32768.0 for x in est], [x.astype(np.float32) / 32768.0 for x in tgt])
-    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)
+    assert np.array_equal(a, b, equal_nan=True) and np.array_equal(a, c, equal_nan=True)  # (4th pair: < 7 frames, SSIM NaN)
+    # one launch over all four pairs groups the frames into other work items than the 2-pair chunks of the pipeline:
+    # the float64 partial sums are regrouped (test_flag_subsets_and_batch_invariance), values agree to rounding
+    np.testing.assert_allclose(a, d, rtol=1e-11, atol=1e-12)
     with pytest.raises(TypeError):
         pipe.run(e32.double(), t32, off)
 
@@ -498,17 +501,21 @@ def _helper_reference_runs():
     return json.load(open(path))
 
 
+@pytest.mark.parametrize("mode", ["dense", "fft"])
 @pytest.mark.parametrize("run_name", ["identity_all_settings", "upsampling_testee_output_48k", "reference_test_py"])
-def test_helper_against_the_reference_orchestrator(tmp_path, monkeypatch, run_name):
+def test_helper_against_the_reference_orchestrator(tmp_path, monkeypatch, run_name, mode):
     """SSR_Eval_Helper.evaluate() against tests/golden/helper_reference_runs.json, the result of the REFERENCE'S
     OWN SSR_Eval_Helper.evaluate() (tests/golden/make_golden_helper.py) on the same synthetic data set: same
     speakers / files / distortion keys in the same order, same extra metrics, same mean-of-means aggregation.
-    Keys whose degraded input is bit-identical to the reference's (subsampling: K3, IIR: K7) are held to the
-    north_star tolerances.  proc_fft_* inputs come from K4, whose float32 FFT differs from the reference's float32
-    dense conv DFT by <= 2e-5 per sample (both carry ~1e-6 relative rounding noise): the bins above the cutoff of
-    such an estimate ARE that noise -- the reference's dense float32 dot products of length 2048 leave a ~4x
-    higher floor than an FFT -- so lsd / log_sispec of these keys move with it (the
-    reference's own value depends on its conv1d backend in the same way)."""
+    ``reference_test_py`` is ssr_eval/test.py:24-36 verbatim (44.1 kHz in / out, scored at 48 kHz, setting_fft 12 kHz).
+
+    mode "dense" (K4d, the reference's dense float32 DFT arithmetic for setting_fft): EVERY key -- proc_fft_* included
+    -- is held to the north_star tolerances (1e-4 on lsd / log_sispec, 1e-3 on ssim).
+    mode "fft" (K4, the fast default): keys whose degraded input is bit-identical to the reference's (subsampling:
+    K3, IIR: K7) are held to the same tolerances; proc_fft_* inputs differ from the reference's by <= 2e-5 per sample
+    but carry the LOWER noise floor of a float32 FFT above the cutoff, which is what lsd / log_sispec of such an
+    estimate measure: measured 0.27 / 0.06 apart when scored directly, 5e-4 / 4e-4 once a
+    polyphase resampling follows K4; bounded here at 0.35 / 0.08."""
     from scipy.io import wavfile
     from scipy.signal import resample_poly as rp
     from ssr_eval_b200 import SSR_Eval_Helper, BasicTestee
@@ -530,7 +537,9 @@ def test_helper_against_the_reference_orchestrator(tmp_path, monkeypatch, run_na
     for k in ("setting_fft", "setting_subsampling", "setting_lowpass_filtering"):
         if k in kwargs:  # the stored kwargs were mutated by the reference's _cutoff2sr: undo the doubling
             kwargs[k] = dict(kwargs[k], cutoff_freq=[c // 2 for c in kwargs[k]["cutoff_freq"]])
-    res = SSR_Eval_Helper(testee, test_name=run_name, test_data_root=str(root), **kwargs).evaluate()
+    helper = SSR_Eval_Helper(testee, test_name=run_name, test_data_root=str(root), **kwargs)
+    helper.stft_hard_mode = mode
+    res = helper.evaluate()
     want = run["result"]
     assert list(res) == list(want)
     worst = {}
@@ -543,15 +552,55 @@ def test_helper_against_the_reference_orchestrator(tmp_path, monkeypatch, run_na
                 got_m, want_m = (a[key], b[key]) if nested else (a, b)
                 assert list(got_m) == list(want_m), (spk, item, key)
                 tol = dict(TOL, n_in=0.0)
-                if key.startswith("proc_fft"):
-                    # measured: lsd 0.27 / log_sispec 0.06 apart when the K4 output is scored directly (identity
-                    # testee), 5e-4 / 4e-4 once a common polyphase resampling follows it; sispec / ssim unaffected
-                    tol.update(lsd=0.5, log_sispec=0.1)
+                if key.startswith("proc_fft") and mode == "fft":
+                    tol.update(lsd=0.35, log_sispec=0.08)
                 for m, w in want_m.items():
                     d = abs(got_m[m] - w)
                     worst[(key, m)] = max(worst.get((key, m), 0.0), d)
-                    assert d <= tol[m], (spk, item, key, m, got_m[m], w)
-    print({k: float("%.2e" % v) for k, v in worst.items()})
+                    assert d <= tol[m], (mode, spk, item, key, m, got_m[m], w)
+    print(mode, {k: float("%.2e" % v) for k, v in worst.items()})
+
+
+def test_dense_stft_hard_lowpass_reproduces_the_reference_arithmetic():
+    """K4d against the oracle (torch's CPU conv1d = what the reference runs): same float32 matrices, same
+    accumulation order -> the waveform is bit-identical for (almost) every sample, and LSD / log-sispec of the
+    low-passed estimate -- which measure the rounding-noise floor above the cutoff -- agree to the metric
+    tolerance, where the float32-FFT kernel K4 is ~0.25 / ~0.05 away."""
+    from ssr_eval_b200 import AudioMetrics, lowpass
+    from ssr_eval_b200.lowpass import stft_hard_lowpass_batch
+    lens = (1025, 30000, 14112, 14113, 2048, 22050)
+    waves = [speech_like(n, sr=44100, seed=180 + i) for i, n in enumerate(lens)]
+    ratios = [0.5, 0.3, 0.9, 1.0, 0.0, 12000 / 22050]
+    got = stft_hard_lowpass_batch(waves, ratios, mode="dense")
+    fast = stft_hard_lowpass_batch(waves, ratios, mode="fft")
+    same = total = 0
+    for x, r, y, z in zip(waves, ratios, got, fast):
+        want = oracle.stft_hard_lowpass_v0(x, r)
+        assert y.shape == want.shape and y.dtype == np.float32
+        assert np.abs(y - want).max() <= 2e-7, (len(x), r, np.abs(y - want).max())
+        same += int((y == want).sum())
+        total += len(want)
+        if len(x) > 8000 and 0.0 < r < 1.0:
+            m_ref = oracle.evaluation(want, x, rate=44100)
+            m_dense = AudioMetrics(44100).evaluation(y, x, None)
+            m_fast = AudioMetrics(44100).evaluation(z, x, None)
+            _assert_metrics(m_dense, m_ref, f"dense mode L={len(x)} r={r:.2f}")
+            print(f"L={len(x)} ratio={r:.3f}: LSD reference {m_ref['lsd']:.4f}  dense {m_dense['lsd']:.4f}  fft {m_fast['lsd']:.4f}")
+    assert same >= 0.98 * total, (same, total)
+    print(f"dense stft_hard: {same}/{total} samples bit-identical to the CPU reference arithmetic")
+    # the dispatcher honours the module-level / per-call switch, utterances <= n_fft/2 are rejected like torchlibrosa does
+    import ssr_eval_b200.lowpass as lp
+    old = lp.STFT_HARD_MODE
+    try:
+        lp.STFT_HARD_MODE = "dense"
+        assert np.array_equal(lowpass(waves[1], 6000, 44100, order=1, _type="stft_hard"),
+                              stft_hard_lowpass_batch([waves[1]], [6000 / 22050], mode="dense")[0])
+    finally:
+        lp.STFT_HARD_MODE = old
+    with pytest.raises(N.NativeError):
+        stft_hard_lowpass_batch([waves[0][:1024]], [0.5], mode="dense")
+    with pytest.raises(ValueError):
+        stft_hard_lowpass_batch([waves[0]], [0.5], mode="exact")
 
 
 def test_float64_estimates_follow_the_reference_promotion(engines):
