@@ -5,7 +5,7 @@ NVFLAGS := -DSSR_WARPLOCAL -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wa
 SRC := ssr_eval_b200/csrc
 OBJ := build/obj
 LIB := ssr_eval_b200/lib/libssr_b200.so
-SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu $(SRC)/stft_splice.cu $(SRC)/sosfiltfilt.cu $(SRC)/pcm.cu $(SRC)/stft_lowpass_dense.cu
+SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu $(SRC)/stft_splice.cu $(SRC)/sosfiltfilt.cu $(SRC)/pcm.cu $(SRC)/stft_lowpass_dense.cu $(SRC)/xcorr_align.cu
 OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(SRCS))
 HDRS := $(wildcard $(SRC)/*.cuh) $(SRC)/stft_tables.hpp include/ssr_b200.h Makefile
 

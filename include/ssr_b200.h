@@ -197,6 +197,19 @@ int ssr_sosfiltfilt_batched(const double* sos_host, int n_sections, const double
  * ------------------------------------------------------------------------------------------ */
 int ssr_pcm16_to_float(const int16_t* src_dev, float* dst_dev, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K8 ("next" row): the alignment step of the mp3 degradation,
+ *   np.argmax(scipy.signal.correlate(decoded, x))            (ssr_eval/eval.py:319; the caller subtracts len(x), :319)
+ * for a batch of equal-length (decoded, x) float32 pairs (eval.py:318 unifies the lengths): FFT cross-correlation
+ * (zero-padded to 2^m >= 2L-1, float32 complex like scipy's own path) + first-maximum argmax over scipy's 'full'
+ * index k = 0 .. 2L-2.  L <= 524288 samples.  The codec itself (the sox binary, eval.py:308-316) is out of scope.
+ * argmax_dev: one int64 per pair.  Any workspace that holds the longest pair works; ssr_xcorr_workspace_bytes = one pass.
+ * ------------------------------------------------------------------------------------------ */
+size_t ssr_xcorr_workspace_bytes(const int64_t* offsets_host, int n);
+int ssr_xcorr_argmax_batched(const float* a_dev, const float* x_dev, const int64_t* offsets_host,
+                             const int64_t* offsets_dev, int n, int64_t* argmax_dev, void* workspace_dev,
+                             size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

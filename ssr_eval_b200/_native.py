@@ -68,6 +68,9 @@ def lib():
     L.ssr_stft_hard_lowpass_dense_workspace_bytes.argtypes = [vp, vp, c_int]
     L.ssr_stft_hard_lowpass_dense_workspace_bytes.restype = c_sz
     L.ssr_stft_hard_lowpass_dense_batched.argtypes = [vp, vp, vp, vp, c_int, vp, vp, vp, c_sz, vp]
+    L.ssr_xcorr_workspace_bytes.argtypes = [vp, c_int]
+    L.ssr_xcorr_workspace_bytes.restype = c_sz
+    L.ssr_xcorr_argmax_batched.argtypes = [vp, vp, vp, vp, c_int, vp, vp, c_sz, vp]
     _lib = L
     return L
 
@@ -106,4 +109,5 @@ EXPORTED_SYMBOLS = (
     "ssr_pcm16_to_float",
     "ssr_lowpass_dense_plan_create", "ssr_lowpass_dense_plan_destroy",
     "ssr_stft_hard_lowpass_dense_workspace_bytes", "ssr_stft_hard_lowpass_dense_batched",
+    "ssr_xcorr_workspace_bytes", "ssr_xcorr_argmax_batched",
 )

@@ -182,6 +182,47 @@ SSR_HD void bfly16_group(C2<T>* x) {
   bfly4<INV>(x[4 * Q0], x[4 * Q0 + 1], x[4 * Q0 + 2], x[4 * Q0 + 3]);
 }
 
+#if defined(__CUDACC__)
+// shared-memory loads the compiler may not sink towards their use (they are issued where they are written): used to
+// fetch the twiddles of a pass AHEAD of the butterflies that need them
+__device__ __forceinline__ C2<double> lds_pinned(const C2<double>* p) {
+  C2<double> r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return r;
+}
+__device__ __forceinline__ C2<float> lds_pinned(const C2<float>* p) {
+  C2<float> r;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return r;
+}
+
+// Second half of a radix-16 DIF pass whose outputs are multiplied by twiddles from a shared table (stride TWS between
+// consecutive q) and stored with stride SS: the last radix-4 stage runs group by group (outputs q0, q0+4, q0+8, q0+12)
+// and the 4 twiddles of the NEXT group are requested before the current group is computed, multiplied and stored.
+// The plain form (load twiddle -> multiply -> store, 15 times) serialises 12 shared-memory latencies at the end of the
+// pass with nothing else for the warp to issue (ncu on K1: ~19 % of all warp time on the short scoreboard).
+// STORE(q, value) is the caller's store of output q.
+template <int TWS, typename T, typename STORE>
+__device__ __forceinline__ void bfly16_second_twiddled(C2<T>* v, const C2<T>* tw, STORE store) {
+  C2<T> w[2][4];
+#pragma unroll
+  for (int q1 = 1; q1 < 4; ++q1) w[0][q1] = lds_pinned(tw + (4 * q1 - 1) * TWS);
+#pragma unroll
+  for (int q0 = 0; q0 < 4; ++q0) {
+    if (q0 < 3) {
+#pragma unroll
+      for (int q1 = 0; q1 < 4; ++q1) w[(q0 + 1) & 1][q1] = lds_pinned(tw + (q0 + 1 + 4 * q1 - 1) * TWS);
+    }
+    bfly4<false>(v[4 * q0], v[4 * q0 + 1], v[4 * q0 + 2], v[4 * q0 + 3]);
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) {
+      const int q = q0 + 4 * q1;
+      store(q, q > 0 ? cmul(v[4 * q0 + q1], w[q0 & 1][q1]) : v[0]);
+    }
+  }
+}
+#endif
+
 template <int R, bool INV, typename T>
 SSR_HD void bfly(C2<T>* x) {
   if (R == 16) {

@@ -13,9 +13,10 @@ __device__ __forceinline__ double ldg_f64_pinned(const double* p) {
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
   return r;
 }
-__device__ __forceinline__ cd lds_cd(const cd* p) {
-  cd r;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+
+__device__ __forceinline__ float ldg_f32_pinned(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
 
@@ -109,8 +110,22 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
   const cd* const t2 = tw2 + j2;
   __syncthreads();
 
-  __shared__ int item_slot;
-  for (int item = next_work_item(next_item, &item_slot); item < n_items; item = next_work_item(next_item, &item_slot)) {
+  // Work items are drawn from the device counter ONE ITEM AHEAD: thread 0 requests the next item when the current one
+  // starts, so the ~1 us atomic round trip hides behind the item's frames, and the CTA knows early enough which samples
+  // to pull towards its L1 for the next item's first frame (the only frame that loads all 2 x 2048 samples).
+#ifndef SSR_K1_ITEM_AHEAD
+  // (drawing the items one ahead -- SSR_K1_ITEM_AHEAD -- hides the atomic round trip and allows prefetching the next
+  // item's first frame, but measured 2 % slower: the extra live state costs more than the latency it hides)
+  __shared__ int item_slot1;
+  for (int item = next_work_item(next_item, &item_slot1); item < n_items; item = next_work_item(next_item, &item_slot1)) {
+#else
+  __shared__ int item_slot[2];
+  if (tid == 0) item_slot[0] = atomicAdd(next_item, 1);
+  __syncthreads();
+  int item_par = 0;
+  for (int item = item_slot[0]; item < n_items; item = item_slot[item_par ^= 1]) {
+    if (tid == 0) item_slot[item_par ^ 1] = atomicAdd(next_item, 1);  // read after this item's barriers
+#endif
     const int p = item_pair[item];
     const int c = item - item_start[p];
     const long long off = offsets[p];
@@ -144,10 +159,20 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
           // the 16 half-window values are requested first (L1 hits, but ~40+ cycles): issued behind the tensor-memory
           // traffic they left the FP64 multiplies below waiting on the long scoreboard (ncu: ~3 % of all warp time)
 #ifndef SSR_K1_WIN_AHEAD
-#define SSR_K1_WIN_AHEAD 8
+#define SSR_K1_WIN_AHEAD 16
 #endif
           constexpr int kWinAhead = SSR_K1_WIN_AHEAD;  // window values requested ahead of the tensor-memory wait
           if (ring_next == f) {
+#ifndef SSR_K1_PRE_REGS
+            // the 4 new samples per signal: their lines were pulled into L1 during the previous frame (prefetch below),
+            // so they are fetched here, next to the tensor-memory and window loads, instead of riding in 8 registers
+            // through passes 2 and 3 of the previous frame (which spilled once the twiddle prefetch needed registers)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              pre_t[i] = ldg_f32_pinned(pt + 128 * (12 + i));
+              pre_e[i] = ldg_f32_pinned(pe + 128 * (12 + i));
+            }
+#endif
             tmem_wait_st();  // the previous frame's ring stores
             unsigned r0[16], r1[16], r2[16], r3[16];
             tmem_ld16(ring + 16 * ((c0 + 0) & 3), r0);
@@ -249,6 +274,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       }
 #pragma unroll
       for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
+#ifdef SSR_K1_PRE_REGS
       if (RING) {
         const long long ns = start + hop;  // the next frame of this item, if it is an interior one
         if (fi + 1 < nf && start >= 0 && ns + N <= L) {
@@ -259,7 +285,22 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
           }
         }
       }
+#endif
       __syncthreads();
+#if defined(SSR_K1_ITEM_AHEAD) && !defined(SSR_K1_NO_NEXT_PREFETCH)
+      if (fi == nf - 1) {
+        // last frame of the item: pull the first frame of the NEXT item (known since this item began) towards L1 / L2,
+        // one 128-byte line per thread (64 lines per signal)
+        const int nxt_item = item_slot[item_par ^ 1];
+        if (nxt_item < n_items) {
+          const int np = item_pair[nxt_item];
+          const long long noff = offsets[np];
+          const long long nL = offsets[np + 1] - noff;
+          const long long nstart = (long long)(nxt_item - item_start[np]) * chunk * hop - N / 2 + (long long)(tid & 63) * 32;
+          if (nstart >= 0 && nstart < nL) prefetch_l1((tid < 64 ? tgt : est) + noff + nstart);
+        }
+      }
+#endif
       // ---- pass 2: sub-transforms of length 128 (stride 8)
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[r] = b2[9 * r];
@@ -269,36 +310,9 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
 #pragma unroll
       for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
 #else
-      // The last radix-4 stage is done group by group (outputs q0, q0+4, q0+8, q0+12), and the 4 twiddles of the NEXT
-      // group are fetched from shared memory before the current group is computed, multiplied and stored: the
-      // straightforward form (load twiddle -> multiply -> store, 15 times) serialised 12 shared-memory latencies
-      // at the end of the pass with nothing else to issue (ncu: ~19 % of all warp time, short scoreboard).
+      // last radix-4 stage group by group with the twiddles of the next group fetched ahead (fft_core.cuh)
       bfly16_first<false>(v);
-      {
-        cd w[2][4];
-        auto fetch = [&](int q0, cd* dst) {
-#pragma unroll
-          for (int q1 = 0; q1 < 4; ++q1) {
-            const int q = q0 + 4 * q1;
-            if (q > 0) dst[q1] = lds_cd(t2 + (q - 1) * 8);
-          }
-        };
-        fetch(0, w[0]);
-        auto group = [&](auto q0c) {
-          constexpr int q0 = decltype(q0c)::value;
-          if (q0 < 3) fetch(q0 + 1, w[(q0 + 1) & 1]);
-          bfly16_group<false, q0>(v);
-#pragma unroll
-          for (int q1 = 0; q1 < 4; ++q1) {
-            const int q = q0 + 4 * q1;
-            b2[9 * q] = q > 0 ? cmul(v[4 * q0 + q1], w[q0 & 1][q1]) : v[0];
-          }
-        };
-        group(std::integral_constant<int, 0>{});
-        group(std::integral_constant<int, 1>{});
-        group(std::integral_constant<int, 2>{});
-        group(std::integral_constant<int, 3>{});
-      }
+      bfly16_second_twiddled<8>(v, t2, [&](int q, cd val) { b2[9 * q] = val; });
 #endif
 #ifdef SSR_WARPLOCAL
       __syncwarp();
@@ -397,9 +411,11 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       lsd_sum = (double)sqrtf(sacc / (float)F);  // torch.mean(dim=3) ** 0.5 in float32
     }
     double vals[7] = {lsd_sum, s_et, s_tt, s_ee, l_et, l_tt, l_ee};
+    // only the sums the compile-time metric set fills are reduced (LSD-only: 1 of 7; the others stay 0)
+    constexpr int kFirst = 0, kLast = (FIXED >= 0 && !(FIXED & 6)) ? 1 : ((FIXED >= 0 && !(FIXED & 2)) ? 4 : 7);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const double r = warp_sum(vals[i]);
+    for (int i = kFirst; i < 7; ++i) {
+      const double r = i < kLast ? warp_sum(vals[i]) : 0.0;
       if (lane == 0) red[warp][i] = r;
     }
     __syncthreads();

@@ -54,10 +54,21 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
   if (tid < 120) tw2[tid] = D.tw[16 * (tid & 7) * ((tid >> 3) + 1)];
   if (tid < R * R) wr_s[tid] = D.wr[tid];
   int ia, ib;
+#ifdef SSR_WARPLOCAL
+  // forward passes 2 / 3 and inverse passes 1 / 2 of a sub-transform block and of its Hermitian-partner block run in
+  // one warp (k1_map.cuh): those two exchanges are warp-local, __syncwarp() instead of a CTA barrier
+  bool special_unused;
+  v2w_thread_butterflies(tid, &ia, &ib, &special_unused);
+  const int blk2 = v2w_pass2_block(tid);
+#define SSR_PFA_SYNC_LOCAL() __syncwarp()
+#else
   v2_thread_butterflies(tid, &ia, &ib);
+  const int blk2 = tid >> 3;
+#define SSR_PFA_SYNC_LOCAL() __syncthreads()
+#endif
   const int j2 = tid & 7;
   cd* const b1 = buf + pad_idx(tid);
-  cd* const b2 = buf + pad_idx((tid >> 3) * 128 + j2);
+  cd* const b2 = buf + pad_idx(blk2 * 128 + j2);
   cd* const b3a = buf + 9 * ia;
   cd* const b3b = buf + 9 * ib;
   const cd* const t2 = tw2 + j2;
@@ -183,11 +194,17 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
         // ---- forward pass 2
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = b2[9 * q];
+#ifdef SSR_PFA_PASS2_SERIAL
         bfly16<false>(v);
         b2[0] = v[0];
 #pragma unroll
         for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
-        __syncthreads();
+#else
+        // last radix-4 stage group by group with the twiddles of the next group fetched ahead (fft_core.cuh)
+        bfly16_first<false>(v);
+        bfly16_second_twiddled<8>(v, t2, [&](int q, cd val) { b2[9 * q] = val; });
+#endif
+        SSR_PFA_SYNC_LOCAL();
         // ---- forward pass 3, Bluestein filter, inverse pass 1: all in registers
         cd* a = v;
         cd* b = v + 8;
@@ -218,7 +235,7 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
           b3a[q] = a[q];
           b3b[q] = b[q];
         }
-        __syncthreads();
+        SSR_PFA_SYNC_LOCAL();
         // ---- inverse pass 2 (the chirp * W_N^{rk} factors of the output stage are pulled towards L1 meanwhile:
         // they are L2 round trips otherwise, and holding them in registers across two passes would spill)
 #pragma unroll

@@ -9,6 +9,9 @@
 //   y = upfirdn(h_padded, x, up, down)[n_pre_remove : n_pre_remove + n_out]   (zero extension)
 // i.e.  y[j] = sum_i x[i] * h[(j + n_pre_remove)*down - n_pre_pad - i*up], accumulated in float32
 // in ascending i with a separate multiply and add -- reproduced here term for term.
+#include <stdlib.h>
+
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -133,10 +136,127 @@ k_resample_tiled(const float* __restrict__ x, const long long* __restrict__ in_o
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_resample_bulk: the production kernel for utterances whose index arithmetic fits 32 bits.  Same per-output
+// float32 operation order as k_resample_tiled (bit-identical to scipy), but
+//   * the input span of the CTA is staged by the TMA engine: ONE cp.async.bulk (global -> shared, completion on an
+//     mbarrier) issued by thread 0 instead of a per-element LDG + bounds test + STS loop (~10 instructions per
+//     staged sample); the threads compute their phases and fetch their taps while the copy is in flight.  Tiles
+//     that touch an end of the utterance (zero extension) or the end of the batch buffer keep the element-wise staging;
+//   * all index arithmetic is 32-bit (ncu on the previous kernel: 129 instructions per output against 63 in the
+//     tap loop -- two 64-bit divisions per thread and the staging loop made up the rest);
+//   * a thread produces R = 16 outputs, so the prologue is amortised over twice as many.
+// c = j * down + half_len is the position of output j on the up-sampled grid (>= 0: n_pre_remove * down - n_pre_pad
+// = half_len by construction), newest input sample i = c / up, phase = c % up.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(b), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int KMAX, int R, bool EXACT>
+__global__ void __launch_bounds__(512)
+k_resample_bulk(const float* __restrict__ x, const long long* __restrict__ in_off, float* __restrict__ y,
+                const long long* __restrict__ out_off, int u0, unsigned up, unsigned down, unsigned half_len, int K,
+                const float* __restrict__ bank, int span, long long x_total) {
+  extern __shared__ __align__(16) float xs_raw[];  // span + 8 floats (alignment slack of the bulk copy)
+  __shared__ __align__(8) unsigned long long bar;
+  const int u = u0 + blockIdx.y;
+  const unsigned n_out = (unsigned)(out_off[u + 1] - out_off[u]);
+  const unsigned TP = blockDim.x;
+  const unsigned jb = blockIdx.x * TP * R;  // first output of this CTA
+  if (jb >= n_out) return;
+  const long long xoff = in_off[u];
+  const int n_in = (int)(in_off[u + 1] - xoff);
+  float* yu = y + out_off[u];
+  const unsigned ib = (jb * down + half_len) / up;      // newest sample of the CTA's first output
+  const int i_base = (int)ib - (K - 1);                 // oldest sample the CTA touches (negative at the start)
+  // the bulk copy needs 16-byte aligned addresses and sizes: copy from the aligned address below the span
+  const long long g0 = xoff + i_base;
+  const int shift = (int)(g0 & 3);
+  const int n_copy = (span + shift + 3) & ~3;
+  const bool bulk = i_base >= 0 && i_base + span <= n_in && g0 - shift + n_copy <= x_total;
+  const float* xs = xs_raw + (bulk ? shift : 0);
+  if (bulk) {
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) bulk_load_1d(xs_raw, x + (g0 - shift), (unsigned)n_copy * 4u, &bar);
+  } else {
+    const float* xu = x + xoff;
+    for (int i = threadIdx.x; i < span; i += TP) {
+      const int gi = i_base + i;
+      xs_raw[i] = (gi >= 0 && gi < n_in) ? __ldg(xu + gi) : 0.f;
+    }
+  }
+  // per-thread phase and taps (overlaps the copy)
+  const unsigned j0 = jb + threadIdx.x;
+  const unsigned c0 = j0 * down + half_len;
+  const unsigned i0 = c0 / up;
+  const unsigned phase = c0 - i0 * up;
+  const int p0 = (int)(i0 - ib) + (K - 1);  // index of the newest sample of output j0 inside xs
+  float h[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) h[k] = (EXACT || k < K) ? __ldg(bank + phase * K + k) : 0.f;
+  const int step = (int)((TP / up) * down);  // input advance per TP outputs (TP % up == 0)
+  if (bulk) mbar_wait(&bar, 0);
+  else __syncthreads();
+  constexpr int G = 4;
+  static_assert(R % G == 0, "R must be a multiple of G");
+#pragma unroll 1
+  for (int r0 = 0; r0 < R; r0 += G) {
+    float acc[G];
+    const float* px[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      acc[g] = 0.f;
+      px[g] = xs + p0 + (r0 + g) * step;
+    }
+#pragma unroll
+    for (int k = KMAX - 1; k >= 0; --k)
+      if (EXACT || k < K) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = __fadd_rn(acc[g], __fmul_rn(px[g][-k], h[k]));
+      }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const unsigned j = j0 + (unsigned)(r0 + g) * TP;
+      if (j < n_out) yu[j] = acc[g];
+    }
+  }
+}
+
 }  // namespace ssr
 
 using namespace ssr;
 
+// SSR_FORCE_OLD_K3=1 routes everything through k_resample_tiled (A/B tests only)
+static bool force_old_k3() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_FORCE_OLD_K3");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 template <typename T>
 static int resample_plan_create(ssr_resample_plan** out, int up, int down, const T* taps_host, int n_taps) {
@@ -246,8 +366,45 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
   }
   if (max_out == 0) return SSR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // tiled kernel: block = smallest multiple of `up` that is >= 256 threads (<= 512), 8 outputs per thread
+  // tiled kernels: block = smallest multiple of `up` that is >= 256 threads (<= 512)
   int TP = plan->up * ((256 + plan->up - 1) / plan->up);
+  {
+    // production path: TMA-staged spans, 32-bit index arithmetic, 16 outputs per thread
+    constexpr int R2 = 16;
+    const long long span2 = ((long long)TP * R2 - 1) * plan->down / plan->up + 2 + plan->K;
+    const long long c_max = (max_out + (long long)TP * R2) * plan->down + plan->half_len;
+    long long max_in = 0;
+    for (int u = 0; u < n; ++u) max_in = std::max<long long>(max_in, in_offsets_host[u + 1] - in_offsets_host[u]);
+    if (TP <= 512 && plan->K <= 48 && (span2 + 8) * (long long)sizeof(float) <= 64 * 1024 && c_max < 0x7fffffffLL &&
+        max_in < 0x7fffffffLL && !force_old_k3()) {
+      const int span = (int)span2;
+      const size_t smem = sizeof(float) * (size_t)(span + 8);
+      const long long x_total = in_offsets_host[n];
+      for (int u0 = 0; u0 < n; u0 += 32768) {
+        int nu = n - u0 < 32768 ? n - u0 : 32768;
+        dim3 grid((unsigned)((max_out + (long long)TP * R2 - 1) / ((long long)TP * R2)), nu);
+        const long long* io = reinterpret_cast<const long long*>(in_offsets_dev);
+        const long long* oo = reinterpret_cast<const long long*>(out_offsets_dev);
+#define SSR_K3B_LAUNCH(KM, EX)                                                                                   \
+  do {                                                                                                           \
+    auto kern = k_resample_bulk<KM, R2, EX>;                                                                     \
+    SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    kern<<<grid, TP, smem, st>>>(x_dev, io, y_dev, oo, u0, (unsigned)plan->up, (unsigned)plan->down,            \
+                                 (unsigned)plan->half_len, plan->K, static_cast<const float*>(plan->bank), span, \
+                                 x_total);                                                                       \
+  } while (0)
+        if (plan->K == 21) SSR_K3B_LAUNCH(21, true);       // 44.1k <-> 48k up (160/147), 16k -> 44.1k (441/160)
+        else if (plan->K == 22) SSR_K3B_LAUNCH(22, true);  // 48k -> 44.1k (147/160)
+        else if (plan->K <= 24) SSR_K3B_LAUNCH(24, false);
+        else if (plan->K <= 32) SSR_K3B_LAUNCH(32, false);
+        else if (plan->K <= 40) SSR_K3B_LAUNCH(40, false);
+        else SSR_K3B_LAUNCH(48, false);
+#undef SSR_K3B_LAUNCH
+        SSR_LAUNCH_CHECK("k_resample_bulk");
+      }
+      return SSR_OK;
+    }
+  }
   constexpr int R = 8;
   // input samples one CTA touches: newest(j_last) - newest(j_first) + K <= (TP*R - 1) * down / up + 1 + K
   const long long span_ll = ((long long)TP * R - 1) * plan->down / plan->up + 2 + plan->K;

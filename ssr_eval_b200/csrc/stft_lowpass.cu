@@ -298,10 +298,9 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
     // ---- forward pass 2
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = b2[8 * r + (r >> 1)];
-    bfly16<false>(v);
-    b2[0] = v[0];
-#pragma unroll
-    for (int q = 1; q < 16; ++q) b2[8 * q + (q >> 1)] = cmul(v[q], t2[(q - 1) * 8]);
+    // last radix-4 stage group by group with the twiddles of the next group fetched ahead (fft_core.cuh)
+    bfly16_first<false>(v);
+    bfly16_second_twiddled<8>(v, t2, [&](int q, cf val) { b2[8 * q + (q >> 1)] = val; });
     SSR_SYNC_LOCAL();
     // ---- forward pass 3 (registers), bin processing, inverse pass 1 (registers)
     cf* a = v;

@@ -220,6 +220,8 @@ static size_t dense_bytes_per_frame(int n_fft, int F) {
   // A (n_fft) + Cfwd (2F) + Dre (n_fft) + Dim (n_fft) + S (n_fft) floats
   return sizeof(float) * ((size_t)4 * n_fft + 2 * (size_t)F);
 }
+// the five arrays of a chunk start on 256-byte boundaries (the sgemm loads float4): slack reserved per chunk
+constexpr size_t kDenseSlack = 5 * 256;
 
 }  // namespace ssr
 
@@ -277,7 +279,7 @@ size_t ssr_stft_hard_lowpass_dense_workspace_bytes(const ssr_lowpass_dense_plan*
   if (!plan || !offsets_host || n < 1) return 0;
   long long frames = 0;
   for (int u = 0; u < n; ++u) frames += (offsets_host[u + 1] - offsets_host[u]) / plan->hop + 1;
-  return align_up(sizeof(long long) * (size_t)(n + 1), 256) + (size_t)frames * dense_bytes_per_frame(plan->n_fft, plan->F) + 1024;
+  return align_up(sizeof(long long) * (size_t)(n + 1), 256) + (size_t)frames * dense_bytes_per_frame(plan->n_fft, plan->F) + kDenseSlack;
 }
 
 int ssr_stft_hard_lowpass_dense_batched(const ssr_lowpass_dense_plan* plan, const float* x_dev, const int64_t* offsets_host,
@@ -295,9 +297,9 @@ int ssr_stft_hard_lowpass_dense_batched(const ssr_lowpass_dense_plan* plan, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long* offs = reinterpret_cast<const long long*>(offsets_dev);
   const size_t head = align_up(sizeof(long long) * (size_t)(n + 1), 256);
-  if (workspace_bytes <= head + 1024) return fail(SSR_ERR_WORKSPACE, "workspace too small");
+  if (workspace_bytes <= head + kDenseSlack) return fail(SSR_ERR_WORKSPACE, "workspace too small");
   const size_t per_frame = dense_bytes_per_frame(N, F);
-  const long long cap = (long long)((workspace_bytes - head - 1024) / per_frame);
+  const long long cap = (long long)((workspace_bytes - head - kDenseSlack) / per_frame);
   unsigned char* ws = static_cast<unsigned char*>(workspace_dev);
   long long* frame_off = reinterpret_cast<long long*>(ws);
   int u0 = 0;
@@ -311,11 +313,17 @@ int ssr_stft_hard_lowpass_dense_batched(const ssr_lowpass_dense_plan* plan, cons
       ++nu;
     }
     if (nu == 0) return fail(SSR_ERR_WORKSPACE, "workspace too small for the longest utterance");
-    float* A = reinterpret_cast<float*>(ws + head);
-    float* Cf = A + (size_t)frames * N;
-    float* Dre = Cf + (size_t)frames * 2 * F;
-    float* Dim = Dre + (size_t)frames * N;
-    float* S = Dim + (size_t)frames * N;
+    unsigned char* p = ws + head;
+    auto carve = [&](size_t floats) {
+      float* r = reinterpret_cast<float*>(p);
+      p += align_up(sizeof(float) * floats, 256);
+      return r;
+    };
+    float* A = carve((size_t)frames * N);
+    float* Cf = carve((size_t)frames * 2 * F);
+    float* Dre = carve((size_t)frames * N);
+    float* Dim = carve((size_t)frames * N);
+    float* S = carve((size_t)frames * N);
     k_dense_setup<<<1, 32, 0, st>>>(offs, u0, nu, hop, frame_off);
     SSR_LAUNCH_CHECK("k_dense_setup");
     k_dense_frames<<<dim3(64, nu), 256, 0, st>>>(x_dev, offs, u0, frame_off, N, hop, A);

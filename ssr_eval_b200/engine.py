@@ -449,6 +449,30 @@ def sosfiltfilt_batch(sos, wav_list):
     return [yh[s:e].copy() for s, e in zip(off[:-1], off[1:])]
 
 
+def xcorr_argmax_batch(a_list, x_list, workspace_bytes=2 << 30):
+    """K8: ``np.argmax(scipy.signal.correlate(a, x))`` for a batch of equal-length float32 pairs (the alignment of the
+    mp3 path, ssr_eval/eval.py:319) -> list of ints (scipy's 'full' index; the lag is index - (len(x) - 1))."""
+    _require_cuda()
+    assert len(a_list) == len(x_list) and len(a_list) > 0
+    for a, x in zip(a_list, x_list):
+        if len(a) != len(x):
+            raise ValueError("xcorr: the two signals of a pair need the same length (%d vs %d)" % (len(a), len(x)))
+        if 2 * len(x) - 1 > (1 << 20):
+            raise ValueError("xcorr: utterances longer than 524288 samples are not supported")
+    a_h, off = pack_ragged([np.asarray(a, dtype=np.float32) for a in a_list], pinned=True)
+    x_h, _ = pack_ragged([np.asarray(x, dtype=np.float32) for x in x_list], pinned=True)
+    a_d, x_d = a_h.cuda(non_blocking=True), x_h.cuda(non_blocking=True)
+    off_d = torch.from_numpy(off).to(a_d.device)
+    n = len(a_list)
+    out = torch.empty(n, dtype=torch.int64, device=a_d.device)
+    need = N.lib().ssr_xcorr_workspace_bytes(_np_ptr(off), n)
+    longest = N.lib().ssr_xcorr_workspace_bytes(_np_ptr(np.array([0, int(np.diff(off).max())], dtype=np.int64)), 1)
+    ws = torch.empty(max(min(int(need), int(workspace_bytes)), int(longest) + 4 * n + 256), dtype=torch.uint8, device=a_d.device)
+    N.check(N.lib().ssr_xcorr_argmax_batched(_ptr(a_d), _ptr(x_d), _np_ptr(off), _ptr(off_d), n, _ptr(out), _ptr(ws),
+                                             ws.numel(), _stream()), "ssr_xcorr_argmax_batched")
+    return [int(v) for v in out.cpu().numpy()]
+
+
 def pcm16_to_float_device(src_dev, out=None):
     """K0: int16 CUDA tensor -> float32 CUDA tensor, x / 32768 (what librosa.load / soundfile.read give the
     reference for a 16-bit wav).  Asynchronous on the current stream."""

@@ -4,7 +4,8 @@ as batch -> GPU: all files of a speaker are degraded in one K4/K3 launch, pushed
 K1/K2 launch sequence.  Results / JSON schema are the reference's (eval.py:175-227).
 
 Out of scope here (external binaries / network): the VCTK download
-(eval.py:102-119), sox (eval.py:133) and mp3 encoding (eval.py:302-325).
+(eval.py:102-119), sox (eval.py:133) and the mp3 codec itself (eval.py:308-316); the alignment that follows the
+codec (eval.py:318-323) is kernel K8, reachable through the ``mp3_codec`` hook.
 """
 import os
 from datetime import datetime
@@ -71,6 +72,10 @@ class SSR_Eval_Helper:
     # otherwise), "fft" = K4 (float32 FFT, fast), "dense" = K4d (the reference's dense float32 DFT arithmetic: the noise
     # floor above the cutoff -- and with it LSD / log-sispec of an unprocessed proc_fft_* input -- is the reference's)
     stft_hard_mode = None
+    # encode / decode round trip of the mp3 degradation: callable (waveform, sr, low_kbps) -> decoded waveform at sr.
+    # The reference shells out to the sox binary (eval.py:308-316), which this package does not; with a codec plugged in
+    # here the rest of the mp3 path (length unification, cross-correlation alignment, key naming) is the reference's.
+    mp3_codec = None
 
     def __init__(self, testee, input_sr, output_sr, evaluation_sr=44100, test_name="test",
                  test_data_root="./datasets/vctk_test", setting_lowpass_filtering=None,
@@ -132,7 +137,16 @@ class SSR_Eval_Helper:
                 for o, y in zip(outs, ys):
                     o[key] = y
         if self.setting_mp3_compression is not None:
-            raise NotImplementedError("mp3 degradation needs the external sox binary (eval.py:302-325); out of scope")
+            if self.mp3_codec is None:
+                raise NotImplementedError(
+                    "mp3 degradation: the encode / decode round trip is an external codec (the reference shells out to "
+                    "sox, eval.py:308-316) and is out of scope here -- set SSR_Eval_Helper.mp3_codec to a callable "
+                    "(waveform, sr, low_kbps) -> decoded waveform; the alignment (eval.py:318-323) then runs on the GPU")
+            for low_kbps in self.setting_mp3_compression["low_kbps"]:
+                key = "proc_mp3_%s_%s" % (low_kbps, sr)
+                decoded = [np.asarray(self.mp3_codec(x, sr, low_kbps), dtype=np.float32) for x in xs]
+                for o, y in zip(outs, self.mp3_align_batch(decoded, xs)):
+                    o[key] = y
         if self.setting_fft is not None:
             keys, ratios = [], []
             for low_rate in self.setting_fft["cutoff_freq"]:
@@ -184,7 +198,32 @@ class SSR_Eval_Helper:
         return self._degrade_only(x, sr, fft=True)
 
     def mp3_encoding(self, file, x, sr):
-        raise NotImplementedError("mp3 degradation needs the external sox binary (eval.py:302-325); out of scope")
+        """eval.py:302-325 with the codec behind ``mp3_codec`` (the reference shells out to sox); ``file`` unused."""
+        if self.mp3_codec is None:
+            raise NotImplementedError("mp3 degradation needs a codec: set SSR_Eval_Helper.mp3_codec (the reference "
+                                      "shells out to the sox binary, eval.py:308-316)")
+        probe = SSR_Eval_Helper.__new__(SSR_Eval_Helper)
+        probe.setting_lowpass_filtering = probe.setting_subsampling = probe.setting_fft = None
+        probe.setting_mp3_compression = self.setting_mp3_compression
+        probe.mp3_codec = self.mp3_codec
+        probe.stft_hard_mode = self.stft_hard_mode
+        return probe._degrade_batch([np.asarray(x)], sr)[0]
+
+    def mp3_align_batch(self, decoded, originals):
+        """The arithmetic half of ``mp3_encoding`` (eval.py:318-323) for a batch: unify the decoded signal's length
+        with the original's, shift it by ``np.argmax(correlate(decoded, x)) - len(x)`` (kernel K8: FFT
+        cross-correlation + argmax on the GPU) and keep the reference's two assertions."""
+        from .engine import xcorr_argmax_batch
+        pairs = [self.unify_length(np.asarray(d, dtype=np.float32), np.asarray(x, dtype=np.float32))
+                 for d, x in zip(decoded, originals)]
+        idx = xcorr_argmax_batch([p[0] for p in pairs], [p[1] for p in pairs])
+        out = []
+        for (d, x), k in zip(pairs, idx):
+            shifted = self.shift(d, k - x.shape[0])
+            assert shifted.shape == x.shape, str((shifted.shape, x.shape))
+            assert np.sum(shifted - x) != 0.0
+            out.append(shifted)
+        return out
 
     # length / alignment helpers of the mp3 path (eval.py:272-300), kept for API completeness
     def shift(self, x, shift):
