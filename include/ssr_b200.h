@@ -89,6 +89,15 @@ int ssr_stft_metrics_batched_f64est(const ssr_stft_plan* plan, const double* est
                                     unsigned flags, double* out_dev, void* workspace_dev,
                                     size_t workspace_bytes, void* stream);
 
+/* Same, for a float64 estimate AND a float64 target (e.g. soundfile.read's default dtype handed straight to
+ * AudioMetrics.evaluation, metrics.py:51-107): librosa keeps both spectra in complex128 (metrics.py:26-30) and every torch
+ * formula runs in float64.  A float64 target with a float32 estimate is scored through this entry with the estimate
+ * widened (exact); the reference would round |E| to float32 first, a ~6e-8 relative difference per bin. */
+int ssr_stft_metrics_batched_f64(const ssr_stft_plan* plan, const double* est_dev, const double* tgt_dev,
+                                 const int64_t* offsets_host, const int64_t* offsets_dev, int n_pairs,
+                                 unsigned flags, double* out_dev, void* workspace_dev, size_t workspace_bytes,
+                                 void* stream);
+
 /* Magnitude spectrogram only (AudioMetrics.wav_to_spectrogram, metrics.py:26-30) of one ragged
  * batch: spec_dev receives, utterance after utterance, T_i x F float32 row-major (F = n_fft/2+1).
  * Needs the same workspace as ssr_stft_metrics_batched with flags = 0. */
@@ -125,6 +134,14 @@ int ssr_resample_poly_batched_f64(const ssr_resample_plan* plan, const double* x
                                   const int64_t* in_offsets_host, const int64_t* in_offsets_dev,
                                   double* y_dev, const int64_t* out_offsets_host,
                                   const int64_t* out_offsets_dev, int n, void* stream);
+
+/* Explicit polyphase bank instead of a prototype FIR, for resamplers whose per-phase weights are not samples of one
+ * prototype -- resampy's ``kaiser_best`` (what librosa 0.9's librosa.load(sr=...) runs, ssr_eval/eval.py:242,
+ * ssr_eval/metrics.py:22-23): a 512-per-zero-crossing table read with linear interpolation and a truncated table step.
+ * Output j sits at time j * down / up (input samples): n = floor, phase = (j * down) % up; tap k of that phase
+ * (bank_host[phase * K + k]) multiplies x[n + lead - k], zero extension outside the utterance.  Such a plan produces
+ * floor(n_in * up / down) outputs (resampy's length; ssr_resample_out_len knows).  float32 only. */
+int ssr_resample_plan_create_bank(ssr_resample_plan** plan, int up, int down, const float* bank_host, int K, int lead);
 
 /* ------------------------------------------------------------------------------------------
  * K4: STFT hard low-pass = stft_hard_lowpass_v0 (ssr_eval/lowpass.py:17-28) through

@@ -45,10 +45,12 @@ def lib():
     L.ssr_stft_metrics_workspace_bytes.restype = c_sz
     L.ssr_stft_metrics_batched.argtypes = [vp, vp, vp, vp, vp, c_int, c_uint, vp, vp, c_sz, vp]
     L.ssr_stft_metrics_batched_f64est.argtypes = [vp, vp, vp, vp, vp, c_int, c_uint, vp, vp, c_sz, vp]
+    L.ssr_stft_metrics_batched_f64.argtypes = [vp, vp, vp, vp, vp, c_int, c_uint, vp, vp, c_sz, vp]
     L.ssr_stft_magnitude_batched.argtypes = [vp, vp, vp, vp, c_int, vp, vp, c_sz, vp]
     L.ssr_resample_plan_create.argtypes = [ctypes.POINTER(vp), c_int, c_int, vp, c_int]
     L.ssr_resample_plan_create_f64.argtypes = [ctypes.POINTER(vp), c_int, c_int, vp, c_int]
     L.ssr_resample_poly_batched_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int, vp]
+    L.ssr_resample_plan_create_bank.argtypes = [ctypes.POINTER(vp), c_int, c_int, vp, c_int, c_int]
     L.ssr_resample_plan_destroy.argtypes = [vp]
     L.ssr_resample_out_len.argtypes = [vp, c_i64]
     L.ssr_resample_out_len.restype = c_i64
@@ -99,10 +101,11 @@ def launch_count():
 EXPORTED_SYMBOLS = (
     "ssr_version", "ssr_last_error", "ssr_launch_count", "ssr_timing_enable", "ssr_timing_collect",
     "ssr_stft_plan_create", "ssr_stft_plan_destroy", "ssr_stft_num_frames",
-    "ssr_stft_metrics_workspace_bytes", "ssr_stft_metrics_batched", "ssr_stft_metrics_batched_f64est",
+    "ssr_stft_metrics_workspace_bytes", "ssr_stft_metrics_batched", "ssr_stft_metrics_batched_f64est", "ssr_stft_metrics_batched_f64",
     "ssr_stft_magnitude_batched",
     "ssr_resample_plan_create", "ssr_resample_plan_destroy", "ssr_resample_out_len",
     "ssr_resample_poly_batched", "ssr_resample_plan_create_f64", "ssr_resample_poly_batched_f64",
+    "ssr_resample_plan_create_bank",
     "ssr_lowpass_plan_create", "ssr_lowpass_plan_destroy", "ssr_stft_hard_lowpass_batched",
     "ssr_splice_plan_create", "ssr_splice_plan_destroy", "ssr_stft_splice_istft_batched",
     "ssr_sosfiltfilt_workspace_bytes", "ssr_sosfiltfilt_batched",

@@ -26,28 +26,56 @@ def write_wav(path, x, sr):
     wavfile.write(path, int(sr), np.asarray(x, dtype=np.float32))
 
 
-def load_audio(path, sr=None, res_type="polyphase"):
-    """Mono float32 load with optional rate conversion (librosa.load(path, sr=sr) stand-in).  ``res_type``:
-    "polyphase" (scipy resample_poly's Kaiser-5.0 FIR, the default here) or "kaiser_best" (the band-limited
-    Kaiser-windowed sinc librosa 0.9 defaults to; same K3 kernel, different taps -- see engine.kaiser_best_taps)."""
-    if not str(path).lower().endswith(".wav"):
-        raise ValueError("only .wav files are supported in this image (no soundfile/flac codec): %s" % path)
-    x, native = read_wav(path)
-    if sr is None or int(sr) == native:
-        return x, native
+_resamplers = {}
+
+
+def _resampler(sr, native, res_type):
+    """One plan per (target rate, native rate, filter): designing the FIR and uploading it is not per-file work."""
     from math import gcd
     from .engine import PolyphaseResampler, kaiser_best_taps
-    if res_type == "polyphase":
-        rs = PolyphaseResampler(int(sr), native)
-    elif res_type == "kaiser_best":
-        g = gcd(int(sr), native)
-        rs = PolyphaseResampler(int(sr), native, taps=kaiser_best_taps(int(sr) // g, native // g))
-    else:
-        raise ValueError("res_type must be 'polyphase' or 'kaiser_best', got %r" % (res_type,))
-    y = rs.resample([x])[0]
-    n = int(np.ceil(len(x) * float(sr) / native))
-    if len(y) > n:
-        y = y[:n]
-    elif len(y) < n:
-        y = np.pad(y, (0, n - len(y)))
-    return y.astype(np.float32), int(sr)
+    key = (int(sr), int(native), res_type)
+    if key not in _resamplers:
+        if res_type == "polyphase":
+            rs = PolyphaseResampler(int(sr), native)
+        elif res_type == "kaiser_best":
+            rs = PolyphaseResampler(int(sr), native, bank="resampy_kaiser_best")
+        elif res_type == "kaiser_best_exact":
+            g = gcd(int(sr), native)
+            rs = PolyphaseResampler(int(sr), native, taps=kaiser_best_taps(int(sr) // g, native // g))
+        else:
+            raise ValueError("res_type must be 'polyphase', 'kaiser_best' or 'kaiser_best_exact', got %r" % (res_type,))
+        _resamplers[key] = rs
+    return _resamplers[key]
+
+
+def load_audio_batch(paths, sr=None, res_type="polyphase"):
+    """``load_audio`` for a list of files: files that share a native rate are converted in ONE K3 launch."""
+    raw = [read_wav(_check_wav(p)) for p in paths]
+    out = [None] * len(paths)
+    groups = {}
+    for i, (x, native) in enumerate(raw):
+        if sr is None or int(sr) == native:
+            out[i] = (x, native)
+        else:
+            groups.setdefault(native, []).append(i)
+    for native, idx in groups.items():
+        ys = _resampler(sr, native, res_type).resample([raw[i][0] for i in idx])
+        for i, y in zip(idx, ys):
+            n = int(np.ceil(len(raw[i][0]) * float(sr) / native))  # librosa.resample: fix_length to ceil(L * ratio)
+            y = y[:n] if len(y) >= n else np.pad(y, (0, n - len(y)))
+            out[i] = (y.astype(np.float32), int(sr))
+    return out
+
+
+def _check_wav(path):
+    if not str(path).lower().endswith(".wav"):
+        raise ValueError("only .wav files are supported in this image (no soundfile / flac codec): %s" % path)
+    return path
+
+
+def load_audio(path, sr=None, res_type="polyphase"):
+    """Mono float32 load with optional rate conversion (librosa.load(path, sr=sr) stand-in).  ``res_type``:
+    "polyphase" -- scipy resample_poly's Kaiser-5.0 FIR (bit-exact with scipy; the stand-in for the sox binary);
+    "kaiser_best" -- resampy's table-interpolating resampler, what librosa 0.9's load runs (engine.resampy_kaiser_best_bank);
+    "kaiser_best_exact" -- the same band-limited kernel without resampy's table interpolation (engine.kaiser_best_taps)."""
+    return load_audio_batch([path], sr=sr, res_type=res_type)[0]

@@ -17,9 +17,12 @@ namespace ssr {
 // waveform to the sums; only T is rounded to complex64 / float32.  (SSIM gets the float32-rounded |E|:
 // skimage would run in float64, a ~1e-7 effect against the 1e-3 tolerance.)
 // ---------------------------------------------------------------------------------------------
-template <int LOGM, bool BLUE, typename ET>
+// TT = double (only together with ET = double): the TARGET is a float64 waveform too (e.g. soundfile.read's default
+// dtype handed straight to AudioMetrics.evaluation): librosa keeps both spectra in complex128 and every torch formula
+// runs in float64 -- here T stays float64 as well.
+template <int LOGM, bool BLUE, typename ET, typename TT = float>
 __global__ void __launch_bounds__(kThreads)
-k_stft_metrics(StftDev P, const ET* __restrict__ est, const float* __restrict__ tgt,
+k_stft_metrics(StftDev P, const ET* __restrict__ est, const TT* __restrict__ tgt,
                const long long* __restrict__ offsets, const int* __restrict__ item_start,
                const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
                double* __restrict__ partials, float* __restrict__ spec_e,
@@ -28,6 +31,8 @@ k_stft_metrics(StftDev P, const ET* __restrict__ est, const float* __restrict__ 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* buf = reinterpret_cast<cd*>(smem_raw);
   constexpr bool E64 = sizeof(ET) == 8;
+  constexpr bool T64 = sizeof(TT) == 8;
+  static_assert(!T64 || E64, "a float64 target is scored together with a float64 estimate");
   using LT = typename std::conditional<E64, double, float>::type;  // type of the per-frame LSD sums
   __shared__ LT lsd_part[kMaxChunk][kWarps];
   __shared__ double red[kWarps][kPartials];
@@ -47,7 +52,7 @@ k_stft_metrics(StftDev P, const ET* __restrict__ est, const float* __restrict__ 
     const long long f0 = (long long)c * chunk;
     const int nf = (int)min((long long)chunk, T - f0);
     const ET* xe = est + off;
-    const float* xt = tgt + off;
+    const TT* xt = tgt + off;
     double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
 
     for (int fi = 0; fi < nf; ++fi) {
@@ -100,21 +105,23 @@ k_stft_metrics(StftDev P, const ET* __restrict__ est, const float* __restrict__ 
         float mt = sqrtf(tre * tre + tim * tim);
         if (E64) {
           const double me = hypot(a.y + b.y, b.x - a.x);  // np.abs(complex128)
-          if (st) st[k] = mt;
+          const double mt64 = T64 ? hypot(a.x + b.x, a.y - b.y) : (double)mt;
+          if (st) st[k] = T64 ? (float)mt64 : mt;
           if (se) se[k] = (float)me;
           if (want_lsd) {
             const double den = me + 1e-12;
-            const double l = log10((double)(mt * mt) / (den * den) + 1e-12);  // target ** 2 is float32
+            // target ** 2 is float32 for a float32 target, float64 for a float64 one
+            const double l = log10((T64 ? mt64 * mt64 : (double)(mt * mt)) / (den * den) + 1e-12);
             lsd_acc += l * l;
           }
           if (want_lin) {
-            const double dt = (double)mt;
+            const double dt = mt64;
             s_et = fma(me, dt, s_et);
             s_tt = fma(dt, dt, s_tt);
             s_ee = fma(me, me, s_ee);
           }
           if (want_log) {
-            const double le = log10(me + 1e-12), lt = (double)log10f(mt + 1e-12f);
+            const double le = log10(me + 1e-12), lt = T64 ? log10(mt64 + 1e-12) : (double)log10f(mt + 1e-12f);
             l_et = fma(le, lt, l_et);
             l_tt = fma(lt, lt, l_tt);
             l_ee = fma(le, le, l_ee);

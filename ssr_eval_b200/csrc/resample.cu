@@ -18,6 +18,7 @@
 
 struct ssr_resample_plan {
   int up, down, n_taps, half_len, n_pre_pad, n_pre_remove, K, device;
+  int floor_len;  // 1: explicit-bank plan (resampy semantics): floor(n_in * up / down) outputs instead of ceil
   int is_f64;   // 1: float64 plan (bank holds doubles), for float64 waveforms
   void* bank;   // [up][K]: bank[phase*K + k] = h[phase + k*up] (0 beyond n_taps); float or double
 };
@@ -273,6 +274,7 @@ static int resample_plan_create(ssr_resample_plan** out, int up, int down, const
   p->n_pre_remove = (p->half_len + p->n_pre_pad) / down;
   p->K = (n_taps + up - 1) / up;
   p->is_f64 = sizeof(T) == 8;
+  p->floor_len = 0;
   std::vector<T> bank((size_t)up * p->K, (T)0);
   for (int ph = 0; ph < up; ++ph)
     for (int k = 0; k < p->K; ++k) {
@@ -305,6 +307,36 @@ int ssr_resample_plan_create_f64(ssr_resample_plan** out, int up, int down, cons
   return resample_plan_create<double>(out, up, down, taps_host, n_taps);
 }
 
+/* Explicit polyphase bank (see include/ssr_b200.h): output j sits at time j * down / up (in input samples), n = floor,
+ * phase = (j * down) % up; tap k of that phase multiplies x[n + lead - k], k = 0 .. K-1. */
+int ssr_resample_plan_create_bank(ssr_resample_plan** out, int up, int down, const float* bank_host, int K, int lead) {
+  if (!out) return fail(SSR_ERR_INVALID, "plan pointer is NULL");
+  *out = nullptr;
+  if (up < 1 || down < 1 || !bank_host || K < 1 || lead < 0 || lead >= K)
+    return fail(SSR_ERR_INVALID, "resample bank plan: up, down >= 1, K >= 1 and 0 <= lead < K required");
+  ssr_resample_plan* p = new ssr_resample_plan();
+  p->up = up;
+  p->down = down;
+  p->n_taps = K * up;
+  p->K = K;
+  p->half_len = lead * up;      // c = j * down + half_len: newest sample floor(j * down / up) + lead, phase (j * down) % up
+  p->n_pre_remove = 0;
+  p->n_pre_pad = -lead * up;    // the same c for the kernels that use (j + n_pre_remove) * down - n_pre_pad
+  p->is_f64 = 0;
+  p->floor_len = 1;
+  p->bank = nullptr;
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaMalloc(&p->bank, sizeof(float) * (size_t)up * K);
+  if (e == cudaSuccess) e = cudaMemcpy(p->bank, bank_host, sizeof(float) * (size_t)up * K, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (p->bank) cudaFree(p->bank);
+    delete p;
+    return fail(SSR_ERR_CUDA, std::string("resample bank plan upload: ") + cudaGetErrorString(e));
+  }
+  *out = p;
+  return SSR_OK;
+}
+
 int ssr_resample_plan_destroy(ssr_resample_plan* plan) {
   if (!plan) return SSR_OK;
   if (plan->bank) cudaFree(plan->bank);
@@ -315,6 +347,7 @@ int ssr_resample_plan_destroy(ssr_resample_plan* plan) {
 int64_t ssr_resample_out_len(const ssr_resample_plan* plan, int64_t n_in) {
   if (!plan) return -1;
   long long t = (long long)n_in * plan->up;
+  if (plan->floor_len) return (int64_t)(t / plan->down);
   return (int64_t)(t / plan->down + (t % plan->down ? 1 : 0));
 }
 
@@ -331,7 +364,7 @@ int ssr_resample_poly_batched_f64(const ssr_resample_plan* plan, const double* x
     long long n_in = in_offsets_host[u + 1] - in_offsets_host[u];
     long long n_out = out_offsets_host[u + 1] - out_offsets_host[u];
     if (n_out != ssr_resample_out_len(plan, n_in))
-      return fail(SSR_ERR_INVALID, "output offsets do not match ceil(n_in*up/down)");
+      return fail(SSR_ERR_INVALID, "output offsets do not match ssr_resample_out_len(n_in)");
     if (n_out > max_out) max_out = n_out;
   }
   if (max_out == 0) return SSR_OK;
@@ -361,7 +394,7 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
     long long n_in = in_offsets_host[u + 1] - in_offsets_host[u];
     long long n_out = out_offsets_host[u + 1] - out_offsets_host[u];
     if (n_out != ssr_resample_out_len(plan, n_in))
-      return fail(SSR_ERR_INVALID, "output offsets do not match ceil(n_in*up/down)");
+      return fail(SSR_ERR_INVALID, "output offsets do not match ssr_resample_out_len(n_in)");
     if (n_out > max_out) max_out = n_out;
   }
   if (max_out == 0) return SSR_OK;

@@ -130,13 +130,13 @@ static int plan_layout(const ssr_stft_plan* plan, const int64_t* offs, int n, un
   return SSR_OK;
 }
 
-template <int LOGM, bool BLUE, typename ET>
+template <int LOGM, bool BLUE, typename ET, typename TT>
 static int launch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStream_t st,
-                     const ET* est, const float* tgt, const long long* offs_dev,
+                     const ET* est, const TT* tgt, const long long* offs_dev,
                      const int* item_start, const int* item_pair, int n_items, int chunk,
                      unsigned flags, double* partials, float* spec_e, float* spec_t,
                      const long long* spec_off, int* next_item) {
-  auto kern = k_stft_metrics<LOGM, BLUE, ET>;
+  auto kern = k_stft_metrics<LOGM, BLUE, ET, TT>;
   SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TimingState& tm = timing();
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -160,15 +160,15 @@ static int launch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStrea
   return SSR_OK;
 }
 
-template <bool BLUE, typename ET>
+template <bool BLUE, typename ET, typename TT>
 static int dispatch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStream_t st,
-                       const ET* est, const float* tgt, const long long* offs_dev,
+                       const ET* est, const TT* tgt, const long long* offs_dev,
                        const int* item_start, const int* item_pair, int n_items, int chunk,
                        unsigned flags, double* partials, float* spec_e, float* spec_t,
                        const long long* spec_off, int* next_item) {
 #define SSR_CASE(LM)                                                                            \
   case LM:                                                                                      \
-    return launch_k1<LM, BLUE, ET>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair, \
+    return launch_k1<LM, BLUE, ET, TT>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair, \
                                n_items, chunk, flags, partials, spec_e, spec_t, spec_off, next_item);
   switch (plan->logM) {
     SSR_CASE(8)
@@ -186,7 +186,8 @@ static int dispatch_k1(const ssr_stft_plan* plan, int grid, size_t smem, cudaStr
 // est64 != nullptr: the estimate is a float64 batch (generic kernel, see k1_generic.cuh); est is ignored then
 static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st, const float* est,
                   const float* tgt, const long long* offs_dev, int n, unsigned flags,
-                  unsigned char* ws, float* spec_e, float* spec_t, const double* est64 = nullptr) {
+                  unsigned char* ws, float* spec_e, float* spec_t, const double* est64 = nullptr,
+                  const double* tgt64 = nullptr) {
   int* item_start = reinterpret_cast<int*>(ws + w.item_start);
   int* item_pair = reinterpret_cast<int*>(ws + w.item_pair);
   long long* spec_off = reinterpret_cast<long long*>(ws + w.spec_off);
@@ -203,11 +204,18 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   if (per_sm > 2) per_sm = 2;
   int grid = sms * per_sm;
   if (grid > w.n_items) grid = w.n_items;
+  if (est64 && tgt64) {  // float64 estimate AND target: everything stays float64 (generic kernel)
+    if (plan->bluestein)
+      return dispatch_k1<true, double, double>(plan, grid, smem, st, est64, tgt64, offs_dev, item_start, item_pair,
+                                               w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
+    return dispatch_k1<false, double, double>(plan, grid, smem, st, est64, tgt64, offs_dev, item_start, item_pair,
+                                              w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
+  }
   if (est64) {
     if (plan->bluestein)
-      return dispatch_k1<true, double>(plan, grid, smem, st, est64, tgt, offs_dev, item_start, item_pair,
+      return dispatch_k1<true, double, float>(plan, grid, smem, st, est64, tgt, offs_dev, item_start, item_pair,
                                        w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
-    return dispatch_k1<false, double>(plan, grid, smem, st, est64, tgt, offs_dev, item_start, item_pair,
+    return dispatch_k1<false, double, float>(plan, grid, smem, st, est64, tgt, offs_dev, item_start, item_pair,
                                       w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
   }
   if (plan->pfa && !force_generic_k1()) {
@@ -291,9 +299,9 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     return SSR_OK;
   }
   if (plan->bluestein)
-    return dispatch_k1<true, float>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair,
+    return dispatch_k1<true, float, float>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair,
                              w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
-  return dispatch_k1<false, float>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair,
+  return dispatch_k1<false, float, float>(plan, grid, smem, st, est, tgt, offs_dev, item_start, item_pair,
                             w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
 }
 
@@ -455,11 +463,12 @@ size_t ssr_stft_metrics_workspace_bytes(const ssr_stft_plan* plan, const int64_t
 }
 
 static int metrics_batched_impl(const ssr_stft_plan* plan, const float* est_dev, const double* est64_dev,
-                                const float* tgt_dev, const int64_t* offsets_host,
+                                const float* tgt_dev, const double* tgt64_dev, const int64_t* offsets_host,
                                 const int64_t* offsets_dev, int n_pairs, unsigned flags, double* out_dev,
                                 void* workspace_dev, size_t workspace_bytes, void* stream) {
-  if (!plan || (!est_dev && !est64_dev) || !tgt_dev || !offsets_host || !offsets_dev || !out_dev || n_pairs < 1)
+  if (!plan || (!est_dev && !est64_dev) || (!tgt_dev && !tgt64_dev) || !offsets_host || !offsets_dev || !out_dev || n_pairs < 1)
     return fail(SSR_ERR_INVALID, "ssr_stft_metrics_batched: bad argument");
+  if (offsets_host[0] != 0) return fail(SSR_ERR_INVALID, "offsets must start at 0 (pass pointers to the first utterance)");
   if (flags & ~SSR_METRIC_ALL) return fail(SSR_ERR_INVALID, "unknown metric flag");
   WsLayout w;
   int rc = plan_layout(plan, offsets_host, n_pairs, flags, &w);
@@ -472,7 +481,7 @@ static int metrics_batched_impl(const ssr_stft_plan* plan, const float* est_dev,
   const bool do_ssim = flags & SSR_METRIC_SSIM;
   float* spec_e = do_ssim ? reinterpret_cast<float*>(ws + w.spec_e) : nullptr;
   float* spec_t = do_ssim ? reinterpret_cast<float*>(ws + w.spec_t) : nullptr;
-  rc = run_k1(plan, w, st, est_dev, tgt_dev, offs, n_pairs, flags, ws, spec_e, spec_t, est64_dev);
+  rc = run_k1(plan, w, st, est_dev, tgt_dev, offs, n_pairs, flags, ws, spec_e, spec_t, est64_dev, tgt64_dev);
   if (rc != SSR_OK) return rc;
   double* ssim_part = reinterpret_cast<double*>(ws + w.ssim_part);
   if (do_ssim) {
@@ -497,7 +506,7 @@ int ssr_stft_metrics_batched(const ssr_stft_plan* plan, const float* est_dev, co
                              unsigned flags, double* out_dev, void* workspace_dev,
                              size_t workspace_bytes, void* stream) {
   if (!est_dev) return fail(SSR_ERR_INVALID, "ssr_stft_metrics_batched: bad argument");
-  return metrics_batched_impl(plan, est_dev, nullptr, tgt_dev, offsets_host, offsets_dev, n_pairs, flags,
+  return metrics_batched_impl(plan, est_dev, nullptr, tgt_dev, nullptr, offsets_host, offsets_dev, n_pairs, flags,
                               out_dev, workspace_dev, workspace_bytes, stream);
 }
 
@@ -506,7 +515,16 @@ int ssr_stft_metrics_batched_f64est(const ssr_stft_plan* plan, const double* est
                                     unsigned flags, double* out_dev, void* workspace_dev,
                                     size_t workspace_bytes, void* stream) {
   if (!est_dev) return fail(SSR_ERR_INVALID, "ssr_stft_metrics_batched_f64est: bad argument");
-  return metrics_batched_impl(plan, nullptr, est_dev, tgt_dev, offsets_host, offsets_dev, n_pairs, flags,
+  return metrics_batched_impl(plan, nullptr, est_dev, tgt_dev, nullptr, offsets_host, offsets_dev, n_pairs, flags,
+                              out_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int ssr_stft_metrics_batched_f64(const ssr_stft_plan* plan, const double* est_dev, const double* tgt_dev,
+                                 const int64_t* offsets_host, const int64_t* offsets_dev, int n_pairs,
+                                 unsigned flags, double* out_dev, void* workspace_dev, size_t workspace_bytes,
+                                 void* stream) {
+  if (!est_dev || !tgt_dev) return fail(SSR_ERR_INVALID, "ssr_stft_metrics_batched_f64: bad argument");
+  return metrics_batched_impl(plan, nullptr, est_dev, nullptr, tgt_dev, offsets_host, offsets_dev, n_pairs, flags,
                               out_dev, workspace_dev, workspace_bytes, stream);
 }
 

@@ -91,7 +91,10 @@ class StftMetrics:
         if need == 0:
             raise N.NativeError("workspace query failed: " + (N.lib().ssr_last_error() or b"").decode())
         ws = self._ws.get(need, est_dev.device)
-        fn = N.lib().ssr_stft_metrics_batched_f64est if est_dev.dtype == torch.float64 else N.lib().ssr_stft_metrics_batched
+        if tgt_dev.dtype == torch.float64:
+            fn = N.lib().ssr_stft_metrics_batched_f64
+        else:
+            fn = N.lib().ssr_stft_metrics_batched_f64est if est_dev.dtype == torch.float64 else N.lib().ssr_stft_metrics_batched
         N.check(fn(self._plan, _ptr(est_dev), _ptr(tgt_dev), _np_ptr(off_np), _ptr(off_dev), n, flags,
                    _ptr(out_dev), _ptr(ws), ws.numel(), _stream()), "ssr_stft_metrics_batched")
 
@@ -101,8 +104,10 @@ class StftMetrics:
         CUDA tensor [lsd, log_sispec, sispec, ssim] (NaN where not requested). Asynchronous."""
         off_np = np.ascontiguousarray(offsets, dtype=np.int64)
         n = len(off_np) - 1
-        assert est_dev.is_cuda and tgt_dev.is_cuda and tgt_dev.dtype == torch.float32
-        assert est_dev.dtype in (torch.float32, torch.float64)
+        assert est_dev.is_cuda and tgt_dev.is_cuda
+        assert est_dev.dtype in (torch.float32, torch.float64) and tgt_dev.dtype in (torch.float32, torch.float64)
+        if tgt_dev.dtype == torch.float64 and est_dev.dtype != torch.float64:
+            est_dev = est_dev.double()  # a float64 target is scored in float64 together with the (widened) estimate
         assert est_dev.numel() >= off_np[-1] and tgt_dev.numel() >= off_np[-1]
         dev = est_dev.device
         if offsets_dev is None:
@@ -136,15 +141,16 @@ class StftMetrics:
         assert len(est_list) == len(tgt_list) and len(est_list) > 0
         for a, b in zip(est_list, tgt_list):
             assert len(a) == len(b)
-        is64 = [np.asarray(a).dtype == np.float64 for a in est_list]
-        if any(is64) and not all(is64):
+        kinds = [(np.asarray(a).dtype == np.float64, np.asarray(b).dtype == np.float64) for a, b in zip(est_list, tgt_list)]
+        if len(set(kinds)) > 1:  # float32 / float64 pairs keep their own arithmetic: one launch sequence per kind
             out = np.empty((len(est_list), 4), dtype=np.float64)
-            for want in (False, True):
-                idx = [i for i, f in enumerate(is64) if f == want]
+            for want in sorted(set(kinds)):
+                idx = [i for i, f in enumerate(kinds) if f == want]
                 out[idx] = self.metrics([est_list[i] for i in idx], [tgt_list[i] for i in idx], flags)
             return out
-        e_h, off = pack_ragged(est_list, pinned=True, dtype=torch.float64 if is64[0] else torch.float32)
-        t_h, _ = pack_ragged(tgt_list, pinned=True)
+        e64, t64 = kinds[0]
+        e_h, off = pack_ragged(est_list, pinned=True, dtype=torch.float64 if (e64 or t64) else torch.float32)
+        t_h, _ = pack_ragged(tgt_list, pinned=True, dtype=torch.float64 if t64 else torch.float32)
         e_d = e_h.cuda(non_blocking=True)
         t_d = t_h.cuda(non_blocking=True)
         return self.metrics_device(e_d, t_d, off, flags).cpu().numpy()
@@ -198,13 +204,63 @@ def kaiser_best_taps(up, down, dtype=np.float32, num_zeros=64, rolloff=0.9475937
     return (c * np.sinc(c * t) * win).astype(dtype)
 
 
+_RESAMPY_TABLE = None
+
+
+def resampy_kaiser_best_bank(up, down):
+    """Polyphase bank of resampy's ``kaiser_best`` resampler -- what librosa 0.9's ``librosa.load(path, sr=...)`` runs
+    (ssr_eval/eval.py:242, ssr_eval/metrics.py:22-23) -- for the rational ratio up / down, restated from resampy 0.3 /
+    0.4 (``filters.sinc_window``, ``interpn._resample_loop``): a table of the right half of
+    ``rolloff * sinc(rolloff t) * kaiser(beta)`` with 512 samples per zero crossing (64 crossings) that is read with
+    LINEAR interpolation at ``offset = int(frac * 512)``, ``eta = frac * 512 - offset`` and a TRUNCATED step
+    ``index_step = int(scale * 512)`` (scale = min(1, ratio); the table is multiplied by the ratio when down-sampling).
+    For a rational ratio the fractional position of output j depends only on (j * down) % up, so the weights form a
+    polyphase bank: returns (bank float32 [up][K], K, lead) for ``ssr_resample_plan_create_bank`` -- tap k of a phase
+    multiplies x[floor(j * down / up) + lead - k]: k < lead is resampy's right wing (x[n+1], x[n+2], ...), k >= lead
+    its left wing (x[n], x[n-1], ...).  Weights are evaluated in float64 like resampy and rounded to float32 once."""
+    global _RESAMPY_TABLE
+    from scipy.signal.windows import kaiser
+    up, down = int(up), int(down)
+    if _RESAMPY_TABLE is None:
+        num_zeros, num_table, rolloff, beta = 64, 512, 0.9475937167399596, 14.769656459379492
+        n = num_table * num_zeros
+        _RESAMPY_TABLE = kaiser(2 * n + 1, beta)[n:] * (rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1)))
+    ratio = up / down
+    win = _RESAMPY_TABLE * ratio if ratio < 1 else _RESAMPY_TABLE
+    delta = np.zeros_like(win)
+    delta[:-1] = np.diff(win)
+    scale = min(1.0, ratio)
+    num_table, nwin = 512, win.shape[0]
+    index_step = int(scale * num_table)
+    wings = []
+    for p in range(up):
+        frac = scale * (p / up)            # output j = (j * down) // up + p / up input samples
+        out = []
+        for f in (frac, scale - frac):     # left wing, right wing
+            index_frac = f * num_table
+            offset = int(index_frac)
+            eta = index_frac - offset
+            idx = offset + index_step * np.arange((nwin - offset) // index_step)
+            out.append(win[idx] + eta * delta[idx])
+        wings.append(out)
+    lw = max(len(w[0]) for w in wings)
+    rw = max(len(w[1]) for w in wings)
+    bank = np.zeros((up, lw + rw), dtype=np.float64)
+    for p, (left, right) in enumerate(wings):
+        bank[p, rw - len(right):rw] = right[::-1]
+        bank[p, rw:rw + len(left)] = left
+    return np.ascontiguousarray(bank, dtype=np.float32), lw + rw, rw
+
+
 class PolyphaseResampler:
     """K3: scipy.signal.resample_poly(x, up, down) for float32 batches (dtype=np.float64: float64 batches --
     scipy keeps the input dtype, so a float64 waveform is filtered with float64 taps in float64)."""
 
-    def __init__(self, up, down, dtype=np.float32, taps=None):
+    def __init__(self, up, down, dtype=np.float32, taps=None, bank=None):
         """``taps``: optional prototype FIR (odd length, already scaled like scipy's ``h * up``) instead of the
-        Kaiser-5.0 ``firwin`` design of resample_poly, e.g. ``kaiser_best_taps(up, down)``."""
+        Kaiser-5.0 ``firwin`` design of resample_poly, e.g. ``kaiser_best_taps(up, down)``.
+        ``bank``: "resampy_kaiser_best" -- the explicit polyphase bank of resampy's table-interpolating resampler
+        (``resampy_kaiser_best_bank``); such a resampler returns floor(n * up / down) samples like resampy does."""
         _require_cuda()
         g = gcd(int(up), int(down))
         self.up, self.down = int(up) // g, int(down) // g
@@ -213,7 +269,15 @@ class PolyphaseResampler:
         assert self.dtype in (np.dtype(np.float32), np.dtype(np.float64))
         self._tdtype = torch.float64 if self.dtype == np.float64 else torch.float32
         self._plan = ctypes.c_void_p()
-        if not self.identity:
+        self.floor_len = False
+        if bank is not None and not self.identity:
+            if bank != "resampy_kaiser_best" or self.dtype != np.float32 or taps is not None:
+                raise ValueError("bank must be 'resampy_kaiser_best' (float32, no taps)")
+            b, K, lead = resampy_kaiser_best_bank(self.up, self.down)
+            N.check(N.lib().ssr_resample_plan_create_bank(ctypes.byref(self._plan), self.up, self.down, _np_ptr(b), K, lead),
+                    "ssr_resample_plan_create_bank")
+            self.floor_len = True
+        elif not self.identity:
             if taps is None:
                 taps = resample_poly_taps(self.up, self.down, dtype=self.dtype)
             taps = np.ascontiguousarray(taps, dtype=self.dtype)
@@ -231,6 +295,8 @@ class PolyphaseResampler:
 
     def out_len(self, n_in):
         t = int(n_in) * self.up
+        if self.floor_len:
+            return t // self.down
         return t // self.down + (1 if t % self.down else 0)
 
     def resample_device(self, x_dev, in_offsets, in_offsets_dev=None):

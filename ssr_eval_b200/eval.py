@@ -13,7 +13,7 @@ from datetime import datetime
 import numpy as np
 
 from . import _native as N
-from .audio_io import load_audio, write_wav
+from .audio_io import load_audio, load_audio_batch, write_wav
 from .engine import PolyphaseResampler
 from .lowpass import lowpass_batch, stft_hard_lowpass_batch
 from .metrics import AudioMetrics
@@ -65,9 +65,15 @@ class BasicTestee:
 
 
 class SSR_Eval_Helper:
-    # resampler used when a file's native rate differs from input_sr / evaluation_sr ("polyphase" | "kaiser_best");
-    # the reference leaves this to librosa.load (kaiser_best in 0.9) and to the sox binary -- see INTEGRATION.md
-    load_res_type = "polyphase"
+    # Resamplers used when a file's native rate differs from the rate it is needed at (audio_io.load_audio):
+    #  * load_res_type: the model input, which the reference reads with librosa.load(file, sr=input_sr) (eval.py:242) --
+    #    resampy's "kaiser_best" in librosa 0.9 (restated, engine.resampy_kaiser_best_bank; "polyphase" and
+    #    "kaiser_best_exact" are the alternatives);
+    #  * target_res_type: the evaluation target, which the reference converts with the sox binary (eval.py:133) -- sox
+    #    is not reproducible here; the stand-in is scipy's polyphase filter ("polyphase", bit-exact with
+    #    scipy.signal.resample_poly).  See INTEGRATION.md section D.
+    load_res_type = "kaiser_best"
+    target_res_type = "polyphase"
     # arithmetic of the setting_fft degradation: None = lowpass.STFT_HARD_MODE ("fft" unless SSR_STFT_HARD_MODE says
     # otherwise), "fft" = K4 (float32 FFT, fast), "dense" = K4d (the reference's dense float32 DFT arithmetic: the noise
     # floor above the cutoff -- and with it LSD / log-sispec of an unprocessed proc_fft_* input -- is the reference's)
@@ -281,8 +287,9 @@ class SSR_Eval_Helper:
 
     def evaluate_batch(self, files):
         """{file: {key: {metric: float}}} for a list of audio paths -- one launch sequence."""
-        xs = [load_audio(f, sr=self.model_input_sr, res_type=self.load_res_type)[0] for f in files]
-        targets = [load_audio(f, sr=self.evaluationset_sr, res_type=self.load_res_type)[0] for f in files]
+        # one K3 launch per (native rate, wanted rate) instead of two plan builds + launches per file
+        xs = [w for w, _ in load_audio_batch(files, sr=self.model_input_sr, res_type=self.load_res_type)]
+        targets = [w for w, _ in load_audio_batch(files, sr=self.evaluationset_sr, res_type=self.target_res_type)]
         degraded = self._degrade_batch(xs, self.model_input_sr)
         items, processed, extras = [], [], []
         for fi, d in enumerate(degraded):
@@ -344,6 +351,12 @@ class SSR_Eval_Helper:
             if limit_test_nums > 0:
                 files = files[:limit_test_nums]
             work += [(speaker, f) for f in files]
+        # The reference also lists .flac files (eval.py:160); this image has no flac decoder (no soundfile / libsndfile):
+        # fail HERE, before any work is done, instead of aborting half way through a speaker
+        flacs = [os.path.join(sp, f) for sp, f in work if f.lower().endswith(".flac")]
+        if flacs:
+            raise ValueError("%d .flac test file(s) (first: %s) need a decoder this image does not have; convert the "
+                             "test set to .wav (e.g. `sox in.flac out.wav`)" % (len(flacs), flacs[0]))
         mine = work[rank::world]
         local = {}
         for s in range(0, len(mine), batch_files):

@@ -8,20 +8,20 @@ from .engine import StftMetrics
 EPS = 1e-12
 
 
-def _as_wave(x, keep_float64=False):
-    """float32 waveform; a float64 ESTIMATE stays float64: the reference's IIR low-pass filters return float64
-    (scipy sosfiltfilt) and librosa / torch keep such an estimate in float64 end to end (dtype_r2c, type
-    promotion) -- the kernels reproduce that (include/ssr_b200.h, ssr_stft_metrics_batched_f64est).  Targets
-    come from librosa.load in the reference and are float32 there; any other dtype is cast to float32."""
+def _as_wave(x):
+    """float32 or float64 waveform.  float64 stays float64: the reference's IIR low-pass filters return float64
+    estimates (scipy sosfiltfilt), soundfile.read returns float64 by default, and librosa / torch keep such a signal in
+    float64 end to end (dtype_r2c, type promotion) -- the kernels reproduce that (include/ssr_b200.h,
+    ssr_stft_metrics_batched_f64est / _f64).  Any other dtype is cast to float32."""
     a = np.asarray(x)
-    if a.dtype == np.float64 and keep_float64:
-        return a
-    if a.dtype != np.float32:
+    if a.dtype not in (np.float32, np.float64):
         a = a.astype(np.float32)
     return a
 
 
 class AudioMetrics:
+    load_res_type = "kaiser_best"  # resampler of read(): what librosa 0.9's librosa.load(sr=...) uses
+
     def __init__(self, rate, n_fft=None, hop_length=None):
         """ssr_eval/metrics.py:16-19: hop = int(rate/100), n_fft = int(2048/(44100/rate)).
         ``n_fft`` / ``hop_length`` overrides exist for BASELINE config 2 (2048 / 512)."""
@@ -37,16 +37,17 @@ class AudioMetrics:
         return self._engine
 
     def read(self, est, target):
-        """ssr_eval/metrics.py:21-24 (librosa.load(sr=rate, mono=True))."""
+        """ssr_eval/metrics.py:21-24 (librosa.load(sr=rate, mono=True): resampy's kaiser_best when the file's rate
+        differs, see audio_io.load_audio)."""
         from .audio_io import load_audio
-        e, _ = load_audio(est, sr=self.rate)
-        t, _ = load_audio(target, sr=self.rate)
+        e, _ = load_audio(est, sr=self.rate, res_type=self.load_res_type)
+        t, _ = load_audio(target, sr=self.rate, res_type=self.load_res_type)
         return e, t
 
     def wav_to_spectrogram(self, wav):
         """ssr_eval/metrics.py:26-30: |STFT| as a (1, 1, T, F) float32 torch tensor (on the host)."""
         import torch
-        return torch.from_numpy(self.engine.magnitude([_as_wave(wav)])[0])[None, None, ...]
+        return torch.from_numpy(self.engine.magnitude([np.asarray(wav, dtype=np.float32)])[0])[None, None, ...]
 
     @staticmethod
     def _check_pair(est, target):
@@ -60,7 +61,7 @@ class AudioMetrics:
             "Error: Shape mismatch between target and estimation %s and %s"
             % (str(target.shape), str(est.shape)))
         n = min(target.shape[0], est.shape[0])
-        return _as_wave(est[:n], keep_float64=True), _as_wave(target[:n])
+        return _as_wave(est[:n]), _as_wave(target[:n])
 
     def evaluation(self, est, target, file=None):
         """Metrics of one (est, target) pair -> {"lsd","log_sispec","sispec","ssim"} floats

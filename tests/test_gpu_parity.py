@@ -28,7 +28,7 @@ TOL_EXACT = {"lsd": 2e-5, "log_sispec": 2e-5, "sispec": 2e-5}
 # whatever the torch thread count -- while the CUDA path agrees with the exact reductions to 3.3e-7
 LONG_TOL = {"lsd": 1e-4, "log_sispec": 3e-4, "sispec": 2e-3, "ssim": 1e-3}
 # proc_fft_* keys scored through the dense stft_hard mode (K4d) against the reference's own run, see the test below
-DENSE_FFT_KEY_TOL = {"lsd": 5e-4, "log_sispec": 1e-3}
+DENSE_FFT_KEY_TOL = {"lsd": 1e-3, "log_sispec": 1e-3}
 
 
 def _assert_metrics(got, want, ctx="", tol=TOL):
@@ -530,7 +530,7 @@ def test_helper_against_the_reference_orchestrator(tmp_path, monkeypatch, run_na
     ``reference_test_py`` is ssr_eval/test.py:24-36 verbatim (44.1 kHz in / out, scored at 48 kHz, setting_fft 12 kHz).
 
     mode "dense" (K4d, the reference's dense float32 DFT arithmetic for setting_fft): proc_fft_* keys are held to
-    DENSE_FFT_KEY_TOL (lsd 5e-4, log_sispec 1e-3; measured <= 1.1e-4 / 2.9e-4) -- every linear stage of K4d is bit-identical
+    DENSE_FFT_KEY_TOL (1e-3 on lsd / log_sispec; measured <= 4.1e-4 / 2.9e-4, 1e-5 when a resampling follows; fft mode: 0.27 / 0.06) -- every linear stage of K4d is bit-identical
     to torch's CPU convolutions, what is left is torch's vectorised float32 sqrt, which is NOT correctly rounded on an
     AVX-512 host (1 ulp low for 0.72 % of its arguments, max error 0.56 ulp; profiles/r02_dense_dft_study.md) and
     changes the rounding noise above the cutoff -- the only thing lsd of such an estimate measures -- at that level.
@@ -585,32 +585,52 @@ def test_helper_against_the_reference_orchestrator(tmp_path, monkeypatch, run_na
 
 
 def test_dense_stft_hard_lowpass_reproduces_the_reference_arithmetic():
-    """K4d against the oracle (torch's CPU conv1d = what the reference runs): same float32 matrices, same
-    accumulation order -> the waveform is bit-identical for (almost) every sample, and LSD / log-sispec of the
-    low-passed estimate -- which measure the rounding-noise floor above the cutoff -- agree to the metric
-    tolerance, where the float32-FFT kernel K4 is ~0.25 / ~0.05 away."""
+    """K4d against tests/golden/dense_lowpass_v1.npz -- the reference arithmetic (torch's CPU conv1d with torchlibrosa's
+    kernels) as the build container's AVX-512 host runs it, whose accumulation order K4d reproduces: the waveform is
+    bit-identical for (almost) every sample (what is left is torch's not-correctly-rounded vectorised sqrt), and LSD /
+    log-sispec of the low-passed estimate -- which measure the rounding-noise floor above the cutoff -- agree to
+    DENSE_FFT_KEY_TOL, where the float32-FFT kernel K4 is ~0.25 / ~0.05 away.  Against the LIVE oracle of the box this
+    test runs on (another CPU may pick another accumulation order: same algorithm, another noise floor) only the
+    waveform is compared, at the float32 noise level."""
+    import os
     from ssr_eval_b200 import AudioMetrics, lowpass
     from ssr_eval_b200.lowpass import stft_hard_lowpass_batch
-    lens = (1025, 30000, 14112, 14113, 2048, 22050)
-    waves = [speech_like(n, sr=44100, seed=180 + i) for i, n in enumerate(lens)]
-    ratios = [0.5, 0.3, 0.9, 1.0, 0.0, 12000 / 22050]
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dense_lowpass_v1.npz"))
+    cases = [(int(n), float(r), int(seed)) for n, r, seed in g["cases"]]
+    waves = [speech_like(n, sr=44100, seed=seed) for n, _, seed in cases]
+    ratios = [r for _, r, _ in cases]
     got = stft_hard_lowpass_batch(waves, ratios, mode="dense")
     fast = stft_hard_lowpass_batch(waves, ratios, mode="fft")
     same = total = 0
-    for x, r, y, z in zip(waves, ratios, got, fast):
-        want = oracle.stft_hard_lowpass_v0(x, r)
+    for i, (x, r, y, z) in enumerate(zip(waves, ratios, got, fast)):
+        want = g["y%d" % i]
         assert y.shape == want.shape and y.dtype == np.float32
-        assert np.abs(y - want).max() <= 2e-7, (len(x), r, np.abs(y - want).max())
-        same += int((y == want).sum())
-        total += len(want)
-        if len(x) > 8000 and 0.0 < r < 1.0:
-            m_ref = oracle.evaluation(want, x, rate=44100)
+        if len(x) > 8000:
+            assert np.abs(y - want).max() <= 1e-7, (len(x), r, np.abs(y - want).max())
+            same += int((y == want).sum())
+            total += len(want)
+        else:
+            # a 3-frame utterance: torch / oneDNN pick another convolution kernel (another accumulation order) for so
+            # small a problem -- same algorithm, float32 noise level (measured 2.3e-7)
+            assert np.abs(y - want).max() <= 1e-6, (len(x), r, np.abs(y - want).max())
+        live = oracle.stft_hard_lowpass_v0(x, r)
+        assert np.abs(y - live).max() <= 1e-6, (len(x), r, np.abs(y - live).max())
+        if len(x) > 8000:
+            m_ref = AudioMetrics(44100).evaluation(want, x, None)
             m_dense = AudioMetrics(44100).evaluation(y, x, None)
             m_fast = AudioMetrics(44100).evaluation(z, x, None)
             _assert_metrics(m_dense, m_ref, f"dense mode L={len(x)} r={r:.2f}", dict(TOL, **DENSE_FFT_KEY_TOL))
-            print(f"L={len(x)} ratio={r:.3f}: LSD reference {m_ref['lsd']:.4f}  dense {m_dense['lsd']:.4f}  fft {m_fast['lsd']:.4f}")
+            assert abs(m_fast["lsd"] - m_ref["lsd"]) > 0.05   # the fast kernel's floor really is another one
+            print(f"L={len(x)} ratio={r:.3f}: LSD reference arithmetic {m_ref['lsd']:.4f}  dense {m_dense['lsd']:.4f}  "
+                  f"fft {m_fast['lsd']:.4f}  (live oracle on this box: {oracle.evaluation(live, x, rate=44100)['lsd']:.4f})")
     assert same >= 0.98 * total, (same, total)
-    print(f"dense stft_hard: {same}/{total} samples bit-identical to the CPU reference arithmetic")
+    print(f"dense stft_hard: {same}/{total} samples bit-identical to the golden reference arithmetic ({str(g['host'])})")
+    # ragged batch incl. ratios 0 / 1 and the shortest legal utterance: finite, right shapes, close to the live oracle
+    lens = (1025, 14112, 14113, 2048)
+    more = [speech_like(n, sr=44100, seed=190 + i) for i, n in enumerate(lens)]
+    for x, r, y in zip(more, (0.9, 1.0, 0.0, 0.25), stft_hard_lowpass_batch(more, [0.9, 1.0, 0.0, 0.25], mode="dense")):
+        assert y.shape == x.shape and np.isfinite(y).all()
+        assert np.abs(y - oracle.stft_hard_lowpass_v0(x, r)).max() <= 1e-6
     # the dispatcher honours the module-level / per-call switch, utterances <= n_fft/2 are rejected like torchlibrosa does
     import ssr_eval_b200.lowpass as lp
     old = lp.STFT_HARD_MODE
@@ -700,7 +720,7 @@ def test_fuzz_stft_sizes_and_ragged_batches_vs_oracle():
 
 
 def test_kaiser_best_load_resampler_vs_scipy_with_the_same_taps(tmp_path):
-    """load_audio(res_type="kaiser_best"): the K3 kernel with a Kaiser-windowed-sinc prototype (engine.kaiser_best_taps)
+    """load_audio(res_type="kaiser_best_exact"): the K3 kernel with a Kaiser-windowed-sinc prototype (engine.kaiser_best_taps)
     instead of resample_poly's firwin design -- bit-exact against scipy's upfirdn fed the same float32 taps (K = 136 ..
     407 taps per output: the one-output-per-thread kernel), and within float32 rounding of torchaudio's documented
     kaiser_best equivalent (tests/test_oracle.py checks the design itself on the CPU)."""
@@ -717,7 +737,7 @@ def test_kaiser_best_load_resampler_vs_scipy_with_the_same_taps(tmp_path):
         assert got.dtype == np.float32 and got.shape == want.shape
         assert np.array_equal(got, want), (orig, new, np.abs(got - want).max())
     wavfile.write(str(tmp_path / "a.wav"), 48000, speech_like(20000, 48000, seed=5))
-    y, sr = load_audio(str(tmp_path / "a.wav"), sr=44100, res_type="kaiser_best")
+    y, sr = load_audio(str(tmp_path / "a.wav"), sr=44100, res_type="kaiser_best_exact")
     z, _ = load_audio(str(tmp_path / "a.wav"), sr=44100)
     assert sr == 44100 and len(y) == len(z) == 18375 and np.abs(y - z).max() > 1e-4  # two different filters
     with pytest.raises(ValueError):
@@ -788,3 +808,59 @@ def test_mp3_path_with_a_plugged_codec():
     h.mp3_codec = None
     with pytest.raises(NotImplementedError):
         h._degrade_batch(xs, 44100)
+
+
+def test_resampy_kaiser_best_load_resampler_vs_the_port(tmp_path):
+    """load_audio(res_type="kaiser_best") -- the default of SSR_Eval_Helper.load_res_type / AudioMetrics.read, i.e. what
+    librosa 0.9's librosa.load(sr=...) does (eval.py:242, metrics.py:22-23): resampy's table-interpolating kaiser_best,
+    run as an explicit polyphase bank on the K3 kernels, against the CPU restatement of resampy's loop
+    (oracle/resampy_port.py; float64 weights, float32 accumulation) -- float32 rounding apart."""
+    from scipy.io import wavfile
+    from oracle import resampy_port
+    from ssr_eval_b200.audio_io import load_audio, load_audio_batch
+    from ssr_eval_b200.engine import PolyphaseResampler
+    for orig, new, L in ((48000, 44100, 2500), (48000, 16000, 3001), (16000, 44100, 1200), (44100, 48000, 2048), (48000, 24000, 999)):
+        x = speech_like(L, orig, seed=orig // 1000 + new // 1000)
+        want = resampy_port.resample(x, orig, new)
+        rs = PolyphaseResampler(new, orig, bank="resampy_kaiser_best")
+        got = rs.resample([x, x[:57]])
+        assert got[0].dtype == np.float32 and got[0].shape == want.shape == (int(L * new / orig),)
+        assert np.abs(got[0] - want).max() <= 1e-6 * max(1.0, np.abs(x).max()), (orig, new, np.abs(got[0] - want).max())
+        assert np.abs(got[1] - resampy_port.resample(x[:57], orig, new)).max() <= 1e-6
+    paths = []
+    for i, (sr, n) in enumerate(((48000, 20001), (48000, 9000), (44100, 7000), (16000, 5000))):
+        paths.append(str(tmp_path / f"f{i}.wav"))
+        wavfile.write(paths[-1], sr, speech_like(n, sr, seed=40 + i))
+    batch = load_audio_batch(paths, sr=44100, res_type="kaiser_best")
+    for p, (y, sr) in zip(paths, batch):
+        native, raw = wavfile.read(p)
+        want = resampy_port.librosa_load_resample(raw, native, 44100)
+        assert sr == 44100 and y.shape == want.shape and np.abs(y - want).max() <= 1e-6
+        one, _ = load_audio(p, sr=44100, res_type="kaiser_best")
+        assert np.array_equal(one, y)
+
+
+def test_float64_targets_are_scored_in_float64(engines):
+    """soundfile.read hands back float64 by default; AudioMetrics.evaluation(est, target) of the reference then keeps
+    BOTH spectra in complex128 and every formula in float64 (metrics.py:26-30, 109-121).  Reproduced by the float64
+    target path (ssr_stft_metrics_batched_f64) instead of a silent cast to float32: a hard-low-passed float64 pair
+    scores differently in the two arithmetics (the stop band is below float32's quantisation noise)."""
+    from ssr_eval_b200 import AudioMetrics
+    for rate, n in ((44100, 22050), (48000, 24000)):
+        t32 = speech_like(n, rate, seed=800 + rate // 1000)
+        t64 = t32.astype(np.float64) * (1.0 + 1e-9)          # a genuinely float64 target
+        e64 = oracle.lowpass(t32, rate // 8, rate, order=8, _type="butter")
+        want = oracle.evaluation(e64, t64, rate=rate)
+        got = AudioMetrics(rate).evaluation(e64, t64, None)
+        _assert_metrics(got, want, f"float64 pair @ {rate}")
+        e32 = (t32 * 0.7 + 1e-3 * np.random.default_rng(1).standard_normal(n)).astype(np.float32)
+        want = oracle.evaluation(e32, t64, rate=rate)        # float32 estimate, float64 target: promoted
+        got = AudioMetrics(rate).evaluation(e32, t64, None)
+        _assert_metrics(got, want, f"float32 estimate, float64 target @ {rate}")
+    m = AudioMetrics(44100)
+    tgt = speech_like(22050, 44100, seed=78)
+    e64 = oracle.lowpass(tgt, 6000, 44100, order=4, _type="cheby1")
+    res = m.evaluation_batch([e64, e64, tgt * np.float32(0.5)], [tgt.astype(np.float64), tgt, tgt])
+    _assert_metrics(res[0], oracle.evaluation(e64, tgt.astype(np.float64), rate=44100), "mixed/f64-f64")
+    _assert_metrics(res[1], oracle.evaluation(e64, tgt, rate=44100), "mixed/f64-f32")
+    _assert_metrics(res[2], oracle.evaluation(tgt * np.float32(0.5), tgt, rate=44100), "mixed/f32-f32")
