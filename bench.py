@@ -449,12 +449,91 @@ def run_gpu(args):
         td.destroy_process_group()
 
 
+def run_cfg5(args):
+    """BASELINE.json configs[4]: VCTK-shaped synthetic set (8 speakers x 300 ragged 2-8 s utterances at 48 kHz), all
+    four metrics at the reference's own 48 kHz STFT setting (n_fft 2229 / hop 480, metrics.py:18-19), utterances
+    sharded i % world over the ranks, ONE all-reduce of the per-speaker sum / count table (eval.py:200-216) per step.
+    STRONG scaling: the 2400 pairs are the whole job whatever N is.  A step = scoring the rank's shard + D2H of the
+    (n, 4) result + the table all-reduce + the mean of speaker means."""
+    import torch
+    import torch.distributed as td
+    from ssr_eval_b200 import _native as N, dist
+    from ssr_eval_b200.engine import StftMetrics, offsets_of
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    speakers, utts = 8, 300
+    rng = np.random.default_rng(5)
+    lengths = (rng.uniform(2.0, 8.0, size=speakers * utts) * 48000).astype(np.int64)
+    speaker_of = np.repeat(np.arange(speakers), utts)
+    ids = dist.shard_indices(len(lengths), rank, world)
+    g = torch.Generator(device=dev)
+    g.manual_seed(50)
+    all_off = offsets_of(lengths)
+    # the SAME synthetic set for every world size (fixed seed), then this rank's shard of it
+    full_t = 0.1 * torch.randn(int(all_off[-1]), generator=g, device=dev)
+    full_e = full_t + 1e-3 * torch.randn(int(all_off[-1]), generator=g, device=dev)
+    tgt = torch.cat([full_t[all_off[i]:all_off[i + 1]] for i in ids])
+    est = torch.cat([full_e[all_off[i]:all_off[i + 1]] for i in ids])
+    del full_t, full_e
+    off = offsets_of(lengths[ids])
+    off_d = torch.from_numpy(off).to(dev)
+    eng = StftMetrics(2229, 480)
+
+    def step():
+        vals = eng.metrics_device(est, tgt, off, N.METRIC_ALL, offsets_dev=off_d).cpu().numpy()
+        sums = np.zeros((speakers, 1, 4))
+        counts = np.zeros((speakers, 1))
+        np.add.at(sums[:, 0, :], speaker_of[ids], vals)
+        np.add.at(counts[:, 0], speaker_of[ids], 1.0)
+        sums, counts = dist.allreduce_table(sums, counts)
+        return dist.mean_of_means(sums, counts)[1][0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        avg = step()
+    launches0 = N.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        avg = step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(dt, op=td.ReduceOp.MAX)
+    dt = float(dt.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "utterance_pairs_per_sec_all_metrics_vctk_shaped_48k", "value": len(lengths) * args.steps / dt,
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "gpu_launches": int(N.launch_count() - launches0),
+            "config": {"workload": "configs[4]: 8 speakers x 300 ragged 2-8 s utterances at 48 kHz, n_fft 2229 hop 480, "
+                                   "lsd+log_sispec+sispec+ssim, utterance-sharded, 1 all-reduce of the speaker table",
+                       "pairs": int(len(lengths)), "n_fft": 2229, "hop": 480,
+                       "timing": "wall clock around K steps incl. D2H of the results and the all-reduce, max over ranks"},
+            "averaged": [float(v) for v in avg]}), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="cfg2 = BASELINE configs[1] (the contract metric, default); cfg5 = configs[4], strong scaling")
     ap.add_argument("--pairs", type=int, default=1024, help="pairs per GPU per step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-pairs-per-core", type=int, default=16)
@@ -464,6 +543,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "cfg5":
+        run_cfg5(args)
     else:
         run_gpu(args)
 

