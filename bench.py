@@ -412,7 +412,10 @@ def run_gpu(args):
         if os.path.exists(traffic_file):
             try:
                 # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, scaled per pair
-                roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_pair"] * n_pairs
+                tj = json.load(open(traffic_file))
+                roofline["traffic"] = tj["dram_bytes_per_pair"] * n_pairs
+                roofline["traffic_source"] = "ncu capture at commit %s (%s), scaled per pair; not re-measured in this run" % (
+                    tj.get("captured_at_commit", "?"), tj.get("source", "?"))
             except Exception:
                 pass
         cpu = None

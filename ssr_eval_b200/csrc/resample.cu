@@ -358,6 +358,8 @@ int ssr_resample_poly_batched_f64(const ssr_resample_plan* plan, const double* x
   if (!plan || !x_dev || !y_dev || !in_offsets_host || !in_offsets_dev || !out_offsets_host ||
       !out_offsets_dev || n < 1)
     return fail(SSR_ERR_INVALID, "ssr_resample_poly_batched_f64: bad argument");
+  if (int rc = check_offsets(in_offsets_host, n, "ssr_resample_poly_batched_f64 (input)")) return rc;
+  if (int rc = check_offsets(out_offsets_host, n, "ssr_resample_poly_batched_f64 (output)")) return rc;
   if (!plan->is_f64) return fail(SSR_ERR_INVALID, "float32 plan used with float64 data");
   long long max_out = 0;
   for (int u = 0; u < n; ++u) {
@@ -389,6 +391,8 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
   if (!plan || !x_dev || !y_dev || !in_offsets_host || !in_offsets_dev || !out_offsets_host ||
       !out_offsets_dev || n < 1)
     return fail(SSR_ERR_INVALID, "ssr_resample_poly_batched: bad argument");
+  if (int rc = check_offsets(in_offsets_host, n, "ssr_resample_poly_batched (input)")) return rc;
+  if (int rc = check_offsets(out_offsets_host, n, "ssr_resample_poly_batched (output)")) return rc;
   long long max_out = 0;
   for (int u = 0; u < n; ++u) {
     long long n_in = in_offsets_host[u + 1] - in_offsets_host[u];

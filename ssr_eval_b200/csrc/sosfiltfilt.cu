@@ -133,6 +133,7 @@ int ssr_sosfiltfilt_batched(const double* sos_host, int n_sections, const double
     return fail(SSR_ERR_INVALID, "ssr_sosfiltfilt_batched: bad argument");
   if (n_sections < 1 || n_sections > kSosMaxSections) return fail(SSR_ERR_INVALID, "1..32 sections supported");
   if (edge < 0) return fail(SSR_ERR_INVALID, "edge must be >= 0");
+  if (int rc = check_offsets(offsets_host, n, "ssr_sosfiltfilt_batched")) return rc;
   long long total = 0;
   for (int u = 0; u < n; ++u) {
     long long L = offsets_host[u + 1] - offsets_host[u];
@@ -155,9 +156,7 @@ int ssr_sosfiltfilt_batched(const double* sos_host, int n_sections, const double
     P.zi0[s] = zi_host[2 * s];
     P.zi1[s] = zi_host[2 * s + 1];
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   int sp = 1;
   while (sp < n_sections) sp *= 2;  // lanes per utterance
   const int warps_needed = (int)(((long long)n * sp + 31) / 32);

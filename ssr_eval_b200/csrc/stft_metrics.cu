@@ -91,8 +91,8 @@ static int plan_layout(const ssr_stft_plan* plan, const int64_t* offs, int n, un
     total_frames += T;
     if (T > max_T) max_T = T;
   }
-  // ~32 work items per resident CTA slot (148 SMs x 4): with dynamic scheduling the tail is at most one item
-  long long want = 148LL * 4 * 32;
+  // ~32 work items per resident CTA slot (SMs x 4): with dynamic scheduling the tail is at most one item
+  long long want = (long long)sm_count() * 4 * 32;
   long long chunk = (total_frames + want - 1) / want;
   if (chunk < 4) chunk = 4;
   if (chunk > kMaxChunk) chunk = kMaxChunk;
@@ -196,9 +196,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
                               item_pair, spec_off);
   SSR_LAUNCH_CHECK("k_setup");
   size_t smem = sizeof(cd) * (size_t)padded_size(plan->M);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   int per_sm = (int)((200 * 1024) / (smem + 4096));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2) per_sm = 2;
@@ -311,7 +309,7 @@ using namespace ssr;
 
 extern "C" {
 
-int ssr_version(void) { return 100; }
+int ssr_version(void) { return 200; }  // 2xx: round-2 ABI (K0, K4d, K8, explicit resampler banks, float64 targets)
 const char* ssr_last_error(void) { return last_error_ref().c_str(); }
 uint64_t ssr_launch_count(void) { return launch_counter().load(); }
 
@@ -468,7 +466,7 @@ static int metrics_batched_impl(const ssr_stft_plan* plan, const float* est_dev,
                                 void* workspace_dev, size_t workspace_bytes, void* stream) {
   if (!plan || (!est_dev && !est64_dev) || (!tgt_dev && !tgt64_dev) || !offsets_host || !offsets_dev || !out_dev || n_pairs < 1)
     return fail(SSR_ERR_INVALID, "ssr_stft_metrics_batched: bad argument");
-  if (offsets_host[0] != 0) return fail(SSR_ERR_INVALID, "offsets must start at 0 (pass pointers to the first utterance)");
+  if (int rc0 = check_offsets(offsets_host, n_pairs, "ssr_stft_metrics_batched")) return rc0;
   if (flags & ~SSR_METRIC_ALL) return fail(SSR_ERR_INVALID, "unknown metric flag");
   WsLayout w;
   int rc = plan_layout(plan, offsets_host, n_pairs, flags, &w);
@@ -534,6 +532,7 @@ int ssr_stft_magnitude_batched(const ssr_stft_plan* plan, const float* x_dev,
                                void* stream) {
   if (!plan || !x_dev || !offsets_host || !offsets_dev || !spec_dev || n < 1)
     return fail(SSR_ERR_INVALID, "ssr_stft_magnitude_batched: bad argument");
+  if (int rc0 = check_offsets(offsets_host, n, "ssr_stft_magnitude_batched")) return rc0;
   WsLayout w;
   int rc = plan_layout(plan, offsets_host, n, 0, &w);
   if (rc != SSR_OK) return rc;

@@ -339,6 +339,7 @@ int ssr_stft_splice_istft_batched(const ssr_splice_plan* plan, const float* x_de
                                   const int32_t* cut_bins_dev, float* y_dev, void* stream) {
   if (!plan || !x_dev || !out_dev || !offsets_host || !offsets_dev || !cut_bins_dev || !y_dev || n < 1)
     return fail(SSR_ERR_INVALID, "ssr_stft_splice_istft_batched: bad argument");
+  if (int rc0 = check_offsets(offsets_host, n, "ssr_stft_splice_istft_batched")) return rc0;
   long long max_len = 0;
   for (int u = 0; u < n; ++u) {
     long long L = offsets_host[u + 1] - offsets_host[u];

@@ -38,6 +38,18 @@ def test_invalid_arguments_return_status_not_crash():
     assert L.ssr_lowpass_plan_create(ctypes.byref(plan), 2000, 441) == 1
     assert L.ssr_resample_plan_create(ctypes.byref(plan), 160, 147, None, 0) == 1
     assert L.ssr_stft_metrics_batched(None, None, None, None, None, 0, 0, None, None, 0, None) == 1
+    # offsets that do not start at 0 (or decrease) are rejected before any device access (they index the workspace)
+    import numpy as np
+    bad = np.array([5, 105, 205], dtype=np.int64)
+    sos = np.array([[1.0, 0, 0, 1, 0, 0]]); zi = np.zeros((1, 2))
+    dummy = ctypes.c_void_p(bad.ctypes.data)  # never dereferenced: the argument checks come first
+    assert L.ssr_sosfiltfilt_batched(sos.ctypes.data, 1, zi.ctypes.data, 9, dummy, bad.ctypes.data, dummy, 2, dummy,
+                                     dummy, 1 << 20, None) == 1
+    assert b"offsets must start at 0" in L.ssr_last_error()
+    dec = np.array([0, 100, 50], dtype=np.int64)
+    assert L.ssr_pcm16_to_float(None, None, 5, None) == 1
+    assert L.ssr_xcorr_workspace_bytes(dec.ctypes.data, 2) == 0
+    assert L.ssr_version() >= 200
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")

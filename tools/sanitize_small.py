@@ -17,8 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from ssr_eval_b200 import _native as N  # noqa: E402
-from ssr_eval_b200.engine import (StftMetrics, PolyphaseResampler, HardLowpass, SpliceIstft,  # noqa: E402
-                                  sosfiltfilt_batch)
+from ssr_eval_b200.engine import (StftMetrics, PolyphaseResampler, HardLowpass, HardLowpassDense, SpliceIstft,  # noqa: E402
+                                  sosfiltfilt_batch, xcorr_argmax_batch, pcm16_to_float_device)
 
 
 def main():
@@ -51,6 +51,18 @@ def main():
     sos = butter(8, 0.3, output="sos")
     y = sosfiltfilt_batch(sos, tgt)
     print("K7 ok", float(np.abs(y[0]).max()), flush=True)
+    # round-2 kernels: K0 (PCM16), K3 with TMA-staged interior tiles (long utterance), K4d (dense), K8 (alignment)
+    pcm = torch.from_numpy(rng.integers(-32768, 32768, size=10001, dtype=np.int16)).cuda()
+    print("K0 ok", float(pcm16_to_float_device(pcm[1:]).abs().max()), flush=True)
+    long = (0.1 * rng.standard_normal(40000)).astype(np.float32)
+    y = PolyphaseResampler(160, 147).resample([long, tgt[0]])
+    print("K3 bulk ok", len(y[0]), flush=True)
+    y = PolyphaseResampler(44100, 48000, bank="resampy_kaiser_best").resample([tgt[0]])
+    print("K3 resampy bank ok", len(y[0]), flush=True)
+    y = HardLowpassDense(2048, 441).apply(tgt[:2], [0.25, 0.5])
+    print("K4d ok", float(np.abs(y[0]).max()), flush=True)
+    k = xcorr_argmax_batch([np.roll(t, 7) for t in tgt], tgt)
+    print("K8 ok", k, flush=True)
     torch.cuda.synchronize()
     print("sanitize_small done; kernel launches:", N.launch_count(), flush=True)
 
