@@ -11,7 +11,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ssr_eval_b200 import _native as N  # noqa: E402
-from ssr_eval_b200.engine import StftMetrics, PolyphaseResampler, HardLowpass, offsets_of  # noqa: E402
+from ssr_eval_b200.engine import (StftMetrics, PolyphaseResampler, HardLowpass, HardLowpassDense, offsets_of,  # noqa: E402
+                                  pcm16_to_float_device)
 
 dev = torch.device("cuda", 0)
 PEAK = 6582.5
@@ -41,7 +42,7 @@ def report(name, ms, units, unit_name, alg_bytes):
 
 
 def main():
-    which = set(sys.argv[1:]) or {"k1", "k1blue", "k3", "k4", "k6", "k7"}
+    which = set(sys.argv[1:]) or {"k0", "k1", "k1_441", "k1blue", "k3", "k4", "k4d", "k6", "k7", "k8"}
     g = torch.Generator(device=dev)
     g.manual_seed(0)
     if "k1" in which:
@@ -57,6 +58,26 @@ def main():
             ms = timeit(lambda: eng.metrics_device(est, tgt, off, flags, offsets_dev=off_d, out=out))
             report(name, ms, n, "pairs", n * (8 * L + 32))
         del tgt, est
+    if "k1_441" in which:
+        # evaluation at 44.1 kHz (metrics.py:18-19: n_fft 2048, hop 441): the 2048 kernel without the sample ring
+        n, L = 1024, 220500
+        tgt = 0.1 * torch.randn(n * L, generator=g, device=dev)
+        est = tgt + 1e-3 * torch.randn(n * L, generator=g, device=dev)
+        off = offsets_of([L] * n)
+        off_d = torch.from_numpy(off).to(dev)
+        eng = StftMetrics(2048, 441)
+        out = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        for flags, name in ((1, "K1 2048/441 LSD (5 s @ 44.1k)"), (15, "K1+K2 2048/441 all four (5 s @ 44.1k)")):
+            ms = timeit(lambda: eng.metrics_device(est, tgt, off, flags, offsets_dev=off_d, out=out))
+            report(name, ms, n, "pairs", n * (8 * L + 32))
+        del tgt, est
+    if "k0" in which:
+        n = 1024 * 240000 * 2
+        pcm = torch.randint(-32768, 32767, (n,), dtype=torch.int16, device=dev)
+        dst = torch.empty(n, dtype=torch.float32, device=dev)
+        ms = timeit(lambda: pcm16_to_float_device(pcm, out=dst))
+        report("K0 pcm16 -> float32 (1024 pairs x 5 s @ 48k, both signals)", ms, 1024, "pairs", 6 * n)
+        del pcm, dst
     if "k1blue" in which:
         n, L = 256, 240000
         tgt = 0.1 * torch.randn(n * L, generator=g, device=dev)
@@ -91,6 +112,39 @@ def main():
         report("K4 stft_hard 2048/441 (5 s @ 44.1k)", ms, n, "utterances", 8 * n * L)
 
 
+    if "k4d" in which:
+        n, L = 64, 220500
+        x = 0.1 * torch.randn(n * L, generator=g, device=dev)
+        lp = HardLowpassDense(2048, 441)
+        off = offsets_of([L] * n)
+        off_d = torch.from_numpy(off).to(dev)
+        cuts = [lp.cut_bin(12000 / 22050)] * n
+        ms = timeit(lambda: lp.apply_device(x, off, cuts, off_d), iters=2, warm=1)
+        frames = n * (L // 441 + 1)
+        flop = 2.0 * frames * 2048 * (2 * 1025 + 2 * 2048)
+        print(json.dumps({"case": "K4d dense stft_hard 2048/441 (5 s @ 44.1k, 64 utterances)", "ms": round(ms, 3),
+                          "utterances_per_s": round(n / (ms * 1e-3), 1), "fp32_TFLOPs": round(flop / (ms * 1e-3) / 1e12, 2)}),
+              flush=True)
+        del x
+    if "k8" in which:
+        import ctypes
+        n, L = 256, 240000
+        a = 0.1 * torch.randn(n * L, generator=g, device=dev)
+        x = torch.roll(a, 1105) + 1e-3 * torch.randn(n * L, generator=g, device=dev)
+        off = offsets_of([L] * n)
+        off_d = torch.from_numpy(off).to(dev)
+        out = torch.empty(n, dtype=torch.int64, device=dev)
+        need = N.lib().ssr_xcorr_workspace_bytes(ctypes.c_void_p(off.ctypes.data), n)
+        ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+        vp = ctypes.c_void_p
+
+        def run8():
+            N.check(N.lib().ssr_xcorr_argmax_batched(vp(a.data_ptr()), vp(x.data_ptr()), vp(off.ctypes.data), vp(off_d.data_ptr()),
+                                                     n, vp(out.data_ptr()), vp(ws.data_ptr()), ws.numel(),
+                                                     vp(torch.cuda.current_stream().cuda_stream)), "ssr_xcorr_argmax_batched")
+        ms = timeit(run8, iters=3, warm=1)
+        report("K8 xcorr argmax (256 pairs x 5 s @ 48k, FFT 2^19)", ms, n, "pairs", n * 8 * L)
+        del a, x, ws
     if "k6" in which:
         import ctypes
         from ssr_eval_b200.engine import SpliceIstft
