@@ -27,7 +27,7 @@ struct ssr_lowpass_plan {
   const float* win;          // float32(hann_periodic[n])
   const float* win_over_n;   // float32(hann[n] / N)
   const float* win_sq;       // float32(hann[n]^2)
-  const float* ws_tab;       // [hop]: overlap-added window^2 of an interior sample m, index m % hop
+  const float* ws_tab;       // [hop]: overlap-added window^2 of an interior sample m, index m % hop; then [hop]: 1 / max(., 1e-11)
   const uint16_t* ppos;      // padded slot of frequency k after the DIF passes
 };
 
@@ -386,27 +386,49 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
   // same order; m / hop and m % hop are tracked with 32-bit counters (m0 = blockIdx.x * chunk_hops * hop + N/2),
   // so the 64-bit divisions and the 4-5 step loop only run for the few samples at the ends of an utterance.
   {
-    int t = N / 2 + tid;
-    int q = t / hop, r = t - q * hop;
+    // Samples [lo, hi) of the item are interior (every frame that can cover them exists): their window sum depends only
+    // on (N/2 + i) % hop and they are multiplied by the tabulated reciprocal -- one FMUL where the IEEE division with
+    // its FCHK slow path, behind a dependent table load, made this loop 36 % of the kernel's warp time (ncu source
+    // page).  The product differs from the quotient by at most 1 ulp, 3 decades below this kernel's distance to the
+    // reference's dense arithmetic.  The few samples at the ends of an utterance keep the exact sum + division.
     const long long q0 = (long long)blockIdx.x * chunk_hops;
-    for (int i = tid; i < span; i += kV2Threads) {
+    long long lo_ll = (long long)(N - hop) - m0, hi_ll = (T - q0) * hop - N / 2;
+    const int lo = (int)max(0LL, min((long long)span, lo_ll));
+    const int hi = (int)max((long long)lo, min((long long)span, hi_ll));
+    auto slow = [&](int i) {
       const long long m = m0 + i;
-      float ws;
-      if (m >= N - hop && q0 + q <= T - 1) {
-        ws = __ldg(P.ws_tab + r);
-      } else {
-        long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
-        long long fb = min(T - 1, m / hop);
-        ws = 0.f;
-        for (long long f = fa; f <= fb; ++f) ws += P.win_sq[m - f * hop];
-      }
-      ws = fmaxf(ws, 1e-11f);
-      y[off + (m - N / 2)] = acc[i] / ws;
-      r += kV2Threads;
-      while (r >= hop) {
-        r -= hop;
-        ++q;
-      }
+      long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
+      long long fb = min(T - 1, m / hop);
+      float ws = 0.f;
+      for (long long f = fa; f <= fb; ++f) ws += P.win_sq[m - f * hop];
+      y[off + (m - N / 2)] = acc[i] / fmaxf(ws, 1e-11f);
+    };
+    for (int i = tid; i < lo; i += kV2Threads) slow(i);
+    for (int i = hi + tid; i < span; i += kV2Threads) slow(i);
+    const float* inv = P.ws_tab + hop;
+    float* yo = y + off + (m0 - N / 2);
+    int i = lo + tid;
+    int r = (N / 2 + i) % hop;
+    const int step = kV2Threads % hop;  // (hop may be smaller than the block)
+    for (; i + 3 * kV2Threads < hi; i += 4 * kV2Threads) {  // four independent table loads in flight
+      int r1 = r + step, r2, r3;
+      if (r1 >= hop) r1 -= hop;
+      r2 = r1 + step;
+      if (r2 >= hop) r2 -= hop;
+      r3 = r2 + step;
+      if (r3 >= hop) r3 -= hop;
+      const float w0 = __ldg(inv + r), w1 = __ldg(inv + r1), w2 = __ldg(inv + r2), w3 = __ldg(inv + r3);
+      yo[i] = acc[i] * w0;
+      yo[i + kV2Threads] = acc[i + kV2Threads] * w1;
+      yo[i + 2 * kV2Threads] = acc[i + 2 * kV2Threads] * w2;
+      yo[i + 3 * kV2Threads] = acc[i + 3 * kV2Threads] * w3;
+      r = r3 + step;
+      if (r >= hop) r -= hop;
+    }
+    for (; i < hi; i += kV2Threads) {
+      yo[i] = acc[i] * __ldg(inv + r);
+      r += step;
+      if (r >= hop) r -= hop;
     }
   }
 }
@@ -494,7 +516,7 @@ int ssr_lowpass_plan_create(ssr_lowpass_plan** out, int n_fft, int hop) {
   size_t o_pos = o;
   o = align_up(o + sizeof(uint16_t) * (size_t)N, 256);
   size_t o_ws = o;
-  o = align_up(o + sizeof(float) * (size_t)hop, 256);
+  o = align_up(o + sizeof(float) * 2 * (size_t)hop, 256);  // [0, hop): the sums, [hop, 2 hop): their clamped reciprocals
   std::vector<unsigned char> host(o, 0);
   cf* tw = reinterpret_cast<cf*>(host.data() + o_tw);
   float* w = reinterpret_cast<float*>(host.data() + o_w);
@@ -517,6 +539,8 @@ int ssr_lowpass_plan_create(ssr_lowpass_plan** out, int n_fft, int hop) {
     volatile float ws = 0.f;
     for (int j = (N - 1 - r) / hop; j >= 0; --j) ws = ws + w2[r + j * hop];
     ws_tab[r] = ws;
+    const float clamped = ws > 1e-11f ? (float)ws : 1e-11f;
+    ws_tab[hop + r] = 1.0f / clamped;
   }
   ssr_lowpass_plan* p = new ssr_lowpass_plan();
   p->n_fft = N;
