@@ -9,7 +9,7 @@ namespace ssr {
 // K2: SSIM of two (T, F) float32 magnitude images, valid 7x7 windows only (skimage crops the
 // 3-pixel border, so the reflect boundary mode of uniform_filter never reaches the mean).
 // One CTA = one tile of kSsimTR x kSsimTC window positions, 128 threads, TWO adjacent columns per
-// thread.  Rows stream through a 4-stage shared row buffer that holds, per column, the PAIR (estimate, target);
+// thread.  Rows stream through a 7-stage shared row buffer that holds, per column, the PAIR (estimate, target);
 // per row a thread forms the horizontal 7-sums of (x, y), (xx, yy) and xy for its two columns (sliding: the
 // second column reuses the first column's inner sum) and updates RUNNING vertical 7-sums: V += h_new -
 // h_oldest, with the last seven h kept in a register ring (unrolled-by-7 loop).  Everything that exists for x
@@ -40,7 +40,9 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   const bool ok0 = (c0 + c) < cols_out, ok1 = (c0 + c + 1) < cols_out;
   const float* E = spec_e + spec_off[p];
   const float* G = spec_t + spec_off[p];
-  constexpr int RB = kSsimTC + 8, STAGES = 4;
+  // 7 stages = the unroll factor of the row loop: the stage a row lives in and the stage the next copy refills are
+  // compile-time constants inside the unrolled body (no wrap-around arithmetic, selects or index registers)
+  constexpr int RB = kSsimTC + 8, STAGES = 7;
   // row buffer: per column the pair (estimate, target) -- the pair is the unit every packed operation below works on
   __shared__ __align__(16) float2 rowbuf[STAGES][RB];
   __shared__ double red[kSsimThreads / 32];
@@ -87,11 +89,10 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   const float* e_next = E + (long long)r0 * F + c0;  // row to be issued next
   const float* g_next = G + (long long)r0 * F + c0;
   int rows_left = r_end - r0;
-  int stage_next = 0;
   constexpr unsigned kStageBytes = RB * sizeof(float2);
-  auto issue_row = [&]() {
+  auto issue_row = [&](int stage) {
     if (rows_left > 0) {
-      const unsigned sb = stage_next * kStageBytes;
+      const unsigned sb = stage * kStageBytes;
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
         if (u < 2 || t < 8) {
@@ -106,13 +107,11 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
       e_next += F;
       g_next += F;
       --rows_left;
-      stage_next = (stage_next + 1 == STAGES) ? 0 : stage_next + 1;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 #pragma unroll
-  for (int k = 0; k < STAGES - 1; ++k) issue_row();
-  int par = 0;  // stage holding the row being consumed
+  for (int k = 0; k < STAGES - 1; ++k) issue_row(k);
 
   for (int rb = r0; rb < r_end; rb += 7) {
 #pragma unroll
@@ -121,7 +120,8 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
       if (r < r_end) {  // uniform across the CTA
         asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
         __syncthreads();  // row r has landed for everyone; row r-1 is fully consumed
-        issue_row();      // refills the stage row r-1 occupied
+        issue_row((s + STAGES - 1) % STAGES);  // refills the stage row r-1 occupied
+        const int par = s;  // row r = rb + s lives in stage s (rb - r0 is a multiple of 7 = STAGES)
         float2 P[8];      // (x, y) of columns c .. c+7
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -165,7 +165,6 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
             if (o == 0 ? ok0 : ok1) acc += S;
           }
         }
-        par = (par + 1 == STAGES) ? 0 : par + 1;
       }
     }
   }
