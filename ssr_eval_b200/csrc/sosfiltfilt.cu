@@ -15,7 +15,7 @@
 // utterance, lane s of the group owns section s and at micro-step t filters sample t - s, taking its input
 // from lane s-1 by a width-SP shuffle.  A warp therefore filters 32 / SP utterances at once (the first
 // version gave every utterance a whole warp and left 32 - S lanes idle: 31 k utt/s at order 8).  Inputs are
-// fetched and outputs stored SP samples at a time per group, the next block of inputs one block ahead.
+// fetched and outputs stored SP samples at a time per group, the inputs eight blocks ahead (register ring).
 // Thousands of utterances run concurrently, which is where the throughput comes from.
 #include <math.h>
 
@@ -35,11 +35,14 @@ struct SosDev {
 };
 
 // odd extension in float32 arithmetic: 2*x[0] - x[edge - i] | x | 2*x[L-1] - x[L - 2 - j]
-__device__ __forceinline__ double ext_sample(const float* __restrict__ x, long long L, int edge, long long i) {
-  if (i < edge) return (double)__fsub_rn(__fmul_rn(2.0f, x[0]), x[edge - i]);
+__device__ __forceinline__ float ext_sample_f32(const float* __restrict__ x, long long L, int edge, long long i) {
+  if (i < edge) return __fsub_rn(__fmul_rn(2.0f, x[0]), x[edge - i]);
   const long long m = i - edge;
-  if (m < L) return (double)x[m];
-  return (double)__fsub_rn(__fmul_rn(2.0f, x[L - 1]), x[L - 2 - (m - L)]);
+  if (m < L) return x[m];
+  return __fsub_rn(__fmul_rn(2.0f, x[L - 1]), x[L - 2 - (m - L)]);
+}
+__device__ __forceinline__ double ext_sample(const float* __restrict__ x, long long L, int edge, long long i) {
+  return (double)ext_sample_f32(x, L, edge, i);
 }
 
 template <int SP>
@@ -79,38 +82,56 @@ k_sosfiltfilt(SosDev P, const float* __restrict__ x, const long long* __restrict
       if (live) first = pass == 0 ? ext_sample(xu, L, edge, 0) : w[n_tot - 1];
       double z0 = __dmul_rn(zi0, first), z1 = __dmul_rn(zi1, first);
       double carry = 0.0;  // x_new of the previous micro-step (input of lane s+1)
-      auto fetch = [&](int base) {
+      // a fetched value stays as it was loaded (float32 in the forward pass, float64 in the backward pass) until it is
+      // used: converting at fetch time would make the fetch itself wait for the load
+      auto fetch = [&](int base, float* vf, double* vd) {
         const int ii = base + s;
-        double v = 0.0;
-        if (ii < nt) v = pass == 0 ? ext_sample(xu, L, edge, ii) : w[nt - 1 - ii];
-        return v;
+        *vf = 0.f;
+        *vd = 0.0;
+        if (ii < nt) {
+          if (pass == 0) *vf = ext_sample_f32(xu, L, edge, ii);
+          else *vd = w[nt - 1 - ii];
+        }
       };
-      double xin_next = fetch(0);
-      const int smax = (int)steps_max;
-      for (int base = 0; base < smax; base += SP) {
-        const double xin = xin_next;
-        xin_next = fetch(base + SP);  // one block ahead: its latency hides behind this block's recursion
+      // Inputs are requested PD blocks (PD * SP samples) ahead through a register ring: a group's loads hit a cache
+      // line of its own utterance (nothing coalesces across groups), and one block ahead left the float -> double
+      // conversion of the loaded sample waiting on the long scoreboard for 45 % of all warp time (ncu source page).
+      constexpr int PD = 8;
+      float xqf[PD];
+      double xqd[PD];
 #pragma unroll
-        for (int j = 0; j < SP; ++j) {
-          const int t = base + j;
-          const double from_prev = __shfl_up_sync(full, carry, 1, SP);
-          const double from_mem = __shfl_sync(full, xin, j, SP);
-          const double x_cur = s == 0 ? from_mem : from_prev;
-          const int idx = t - s;  // sample this lane filters now
-          // branch-free step: every lane computes, inactive lanes keep their state and pass on 0
-          const bool act = owner && (unsigned)idx < (unsigned)nt;
-          const double xn = __dadd_rn(__dmul_rn(b0, x_cur), z0);
-          const double z0n = __dadd_rn(__dsub_rn(__dmul_rn(b1, x_cur), __dmul_rn(a1, xn)), z1);
-          const double z1n = __dsub_rn(__dmul_rn(b2, x_cur), __dmul_rn(a2, xn));
-          z0 = act ? z0n : z0;
-          z1 = act ? z1n : z1;
-          carry = act ? xn : 0.0;
-          if (act && s == S - 1) {  // the last section's lane stores output `idx` itself
-            if (pass == 0) {
-              w[idx] = xn;
-            } else {
-              const int m = nt - 1 - idx - edge;  // reverse + strip the padding
-              if ((unsigned)m < (unsigned)Li) yu[m] = xn;
+      for (int b = 0; b < PD; ++b) fetch(b * SP, &xqf[b], &xqd[b]);
+      const int smax = (int)steps_max;
+      for (int base0 = 0; base0 < smax; base0 += SP * PD) {
+#pragma unroll
+        for (int b = 0; b < PD; ++b) {
+          const int base = base0 + b * SP;
+          if (base < smax) {  // uniform across the warp
+            const double xin = pass == 0 ? (double)xqf[b] : xqd[b];
+            fetch(base + PD * SP, &xqf[b], &xqd[b]);
+#pragma unroll
+            for (int j = 0; j < SP; ++j) {
+              const int t = base + j;
+              const double from_prev = __shfl_up_sync(full, carry, 1, SP);
+              const double from_mem = __shfl_sync(full, xin, j, SP);
+              const double x_cur = s == 0 ? from_mem : from_prev;
+              const int idx = t - s;  // sample this lane filters now
+              // branch-free step: every lane computes, inactive lanes keep their state and pass on 0
+              const bool act = owner && (unsigned)idx < (unsigned)nt;
+              const double xn = __dadd_rn(__dmul_rn(b0, x_cur), z0);
+              const double z0n = __dadd_rn(__dsub_rn(__dmul_rn(b1, x_cur), __dmul_rn(a1, xn)), z1);
+              const double z1n = __dsub_rn(__dmul_rn(b2, x_cur), __dmul_rn(a2, xn));
+              z0 = act ? z0n : z0;
+              z1 = act ? z1n : z1;
+              carry = act ? xn : 0.0;
+              if (act && s == S - 1) {  // the last section's lane stores output `idx` itself
+                if (pass == 0) {
+                  w[idx] = xn;
+                } else {
+                  const int m = nt - 1 - idx - edge;  // reverse + strip the padding
+                  if ((unsigned)m < (unsigned)Li) yu[m] = xn;
+                }
+              }
             }
           }
         }

@@ -131,10 +131,9 @@ k_stft_splice_istft_2048(SpDev P, const float* __restrict__ xin, const float* __
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = b2[9 * r];
-        bfly16<false>(v);
-        b2[0] = v[0];
-#pragma unroll
-        for (int q = 1; q < 16; ++q) b2[9 * q] = cmul(v[q], t2[(q - 1) * 8]);
+        // last radix-4 stage group by group with the twiddles of the next group fetched ahead (fft_core.cuh)
+        bfly16_first<false>(v);
+        bfly16_second_twiddled<8>(v, t2, [&](int q, cd val) { b2[9 * q] = val; });
         __syncthreads();
         cd* a = v;
         cd* b = v + 8;
@@ -237,28 +236,49 @@ k_stft_splice_istft_2048(SpDev P, const float* __restrict__ xin, const float* __
   // order, indexed by m % hop through 32-bit counters (m0 = blockIdx.x * chunk_hops * hop + N/2); only the ends
   // of an utterance run the 64-bit divisions and the loop.
   {
-    int t = N / 2 + tid;
-    int q = t / hop, r = t - q * hop;
+    // interior samples [lo, hi) of the item: multiplied by the tabulated reciprocal of the window sum (<= 1 ulp from the
+    // quotient; the division behind a dependent table load was ~6 % of this kernel); the ends of an utterance keep the
+    // exact sum and division (see K4, stft_lowpass.cu)
     const long long q0 = (long long)blockIdx.x * chunk_hops;
-    for (int i = tid; i < span; i += kV2Threads) {
+    const long long lo_ll = (long long)(N - hop) - m0, hi_ll = (T - q0) * hop - N / 2;
+    const int lo = (int)max(0LL, min((long long)span, lo_ll));
+    const int hi = (int)max((long long)lo, min((long long)span, hi_ll));
+    auto slow = [&](int i) {
       const long long m = m0 + i;
-      float ws;
-      if (m >= N - hop && q0 + q <= T - 1) {
-        ws = __ldg(P.ws_tab + r);
-      } else {
-        long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
-        long long fb = min(T - 1, m / hop);
-        ws = 0.f;
-        for (long long f = fa; f <= fb; ++f) ws = (float)((double)ws + __ldg(P.win_sq + (m - f * hop)));
-      }
+      long long fa = (m - N >= 0) ? (m - N) / hop + 1 : 0;
+      long long fb = min(T - 1, m / hop);
+      float ws = 0.f;
+      for (long long f = fa; f <= fb; ++f) ws = (float)((double)ws + __ldg(P.win_sq + (m - f * hop)));
       float val = acc[i];
       if (ws > 1.17549435e-38f) val = val / ws;
       y[off + (m - N / 2)] = val;
-      r += kV2Threads;
-      while (r >= hop) {
-        r -= hop;
-        ++q;
-      }
+    };
+    for (int i = tid; i < lo; i += kV2Threads) slow(i);
+    for (int i = hi + tid; i < span; i += kV2Threads) slow(i);
+    const float* inv = P.ws_tab + hop;
+    float* yo = y + off + (m0 - N / 2);
+    int i = lo + tid;
+    int r = (N / 2 + i) % hop;
+    const int step = kV2Threads % hop;
+    for (; i + 3 * kV2Threads < hi; i += 4 * kV2Threads) {
+      int r1 = r + step, r2, r3;
+      if (r1 >= hop) r1 -= hop;
+      r2 = r1 + step;
+      if (r2 >= hop) r2 -= hop;
+      r3 = r2 + step;
+      if (r3 >= hop) r3 -= hop;
+      const float w0 = __ldg(inv + r), w1 = __ldg(inv + r1), w2 = __ldg(inv + r2), w3 = __ldg(inv + r3);
+      yo[i] = acc[i] * w0;
+      yo[i + kV2Threads] = acc[i + kV2Threads] * w1;
+      yo[i + 2 * kV2Threads] = acc[i + 2 * kV2Threads] * w2;
+      yo[i + 3 * kV2Threads] = acc[i + 3 * kV2Threads] * w3;
+      r = r3 + step;
+      if (r >= hop) r -= hop;
+    }
+    for (; i < hi; i += kV2Threads) {
+      yo[i] = acc[i] * __ldg(inv + r);
+      r += step;
+      if (r >= hop) r -= hop;
     }
   }
 }
@@ -285,7 +305,7 @@ int ssr_splice_plan_create(ssr_splice_plan** out, int n_fft, int hop) {
   size_t o_w2 = o;
   o = align_up(o + sizeof(double) * (size_t)N, 256);
   size_t o_ws = o;
-  o = align_up(o + sizeof(float) * (size_t)hop, 256);
+  o = align_up(o + sizeof(float) * 2 * (size_t)hop, 256);  // [0, hop): the sums, [hop, 2 hop): their reciprocals
   std::vector<unsigned char> host(o, 0);
   cd* tw = reinterpret_cast<cd*>(host.data() + o_tw);
   double* wh = reinterpret_cast<double*>(host.data() + o_wh);
@@ -304,6 +324,7 @@ int ssr_splice_plan_create(ssr_splice_plan** out, int n_fft, int hop) {
     volatile float ws = 0.f;
     for (int j = (N - 1 - r) / hop; j >= 0; --j) ws = (float)((double)ws + w2[r + j * hop]);
     ws_tab[r] = ws;
+    ws_tab[hop + r] = ws > 1.17549435e-38f ? 1.0f / (float)ws : 1.0f;  // librosa divides only where the sum is > tiny
   }
   ssr_splice_plan* p = new ssr_splice_plan();
   p->n_fft = N;
