@@ -19,6 +19,8 @@ __device__ __forceinline__ float ldg_f32_pinned(const float* p) {
   asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
+__device__ __forceinline__ float ldg_pinned(const float* p) { return ldg_f32_pinned(p); }
+__device__ __forceinline__ double ldg_pinned(const double* p) { return ldg_f64_pinned(p); }
 
 // ---------------------------------------------------------------------------------------------
 // K1, specialised: n_fft = 2048 (BASELINE config 2 and every evaluation at 44.1 kHz).
@@ -43,9 +45,12 @@ __device__ __forceinline__ float ldg_f32_pinned(const float* p) {
 // 15 = those + spectrograms.  FIXED < 0: run-time flags.
 
 
-template <int FIXED, bool RING>
+// ET = double: the ESTIMATE is a float64 waveform (the reference's IIR low-pass keys, see k1_generic.cuh): E stays
+// float64 from the waveform to the sums, only T is rounded to complex64 / float32 -- the arithmetic of the generic
+// kernel's float64-estimate path on this kernel's machinery.
+template <int FIXED, bool RING, typename ET = float>
 __global__ void __launch_bounds__(kV2Threads, 4)
-k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __restrict__ tgt,
+k_stft_metrics_2048(StftDev P, const ET* __restrict__ est, const float* __restrict__ tgt,
                     const long long* __restrict__ offsets, const int* __restrict__ item_start,
                     const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
                     double* __restrict__ partials, float* __restrict__ spec_e,
@@ -58,7 +63,9 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
   float* const row_t = reinterpret_cast<float*>(smem_raw + sizeof(cd) * (N + N / 8));  // magnitude rows (store mode)
   float* const row_e = row_t + 1104;
   __shared__ __align__(16) cd tw2[15 * 8];
-  __shared__ float lsd_part[kMaxChunk][NW];
+  constexpr bool E64 = sizeof(ET) == 8;
+  using LT = typename std::conditional<E64, double, float>::type;  // type of the per-frame LSD sums
+  __shared__ LT lsd_part[kMaxChunk][NW];
   __shared__ double red[NW][kPartials];
   __shared__ unsigned tmem_slot;
 
@@ -133,16 +140,20 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
     const long long T = stft_frames(L, N, hop);
     const long long f0 = (long long)c * chunk;
     const int nf = (int)min((long long)chunk, T - f0);
-    const float* xe = est + off;
+    const ET* xe = est + off;
     const float* xt = tgt + off;
     double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
     float* pend_t = nullptr;
     float* pend_e = nullptr;
 
     long long ring_next = -1;  // RING: frame whose 12 older sample blocks sit in the tensor-memory ring
-    float pre_t[4], pre_e[4];  // RING: that frame's 4 new samples per signal, loaded one frame ahead
+    float pre_t[4];  // RING: the frame's 4 new samples per signal
+    ET pre_e[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pre_t[i] = pre_e[i] = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      pre_t[i] = 0.f;
+      pre_e[i] = (ET)0;
+    }
     for (int fi = 0; fi < nf; ++fi) {
       const long long f = f0 + fi;
       const long long start = f * hop - N / 2;
@@ -150,7 +161,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       // ---- pass 1: load + window, radix-16, twiddle, store
       if (start >= 0 && start + N <= L) {
         const float* pt = xt + start + tid;
-        const float* pe = xe + start + tid;
+        const ET* pe = xe + start + tid;
         if (RING) {
           // sample block r of frame f is global block 4 f - 8 + r (blocks of 128 samples); it lives in ring
           // chunk (f + 2 + r / 4) mod 4 (4 blocks x (target, est) x float64 = 16 columns per chunk)
@@ -170,7 +181,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               pre_t[i] = ldg_f32_pinned(pt + 128 * (12 + i));
-              pre_e[i] = ldg_f32_pinned(pe + 128 * (12 + i));
+              pre_e[i] = ldg_pinned(pe + 128 * (12 + i));
             }
 #endif
             tmem_wait_st();  // the previous frame's ring stores
@@ -226,23 +237,40 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
         if (tid < 32) {
           // next frame's new samples: [start + N, start + N + hop) of both signals, one 128 B line per lane
           const long long nxt = start + N + (long long)(tid & 15) * 32;
-          if (nxt < L && (tid & 15) * 32 < hop) prefetch_l1((tid < 16 ? xt : xe) + nxt);
+          if (nxt < L && (tid & 15) * 32 < hop) {
+            if (tid < 16) prefetch_l1(xt + nxt);
+            else prefetch_l1(xe + nxt);  // (a float64 estimate: every other line; the rest come in with the loads)
+          }
         }
       } else {
         // edge frame (reflect padding; < 1 % of the frames): gather through a small staging array so
         // the 64-bit reflect arithmetic stays out of the unrolled hot path
         __syncthreads();  // the staging area aliases buf: the previous frame's pass-3 loads must be done
+        if (E64) {
+          // (float64 estimate: no float2 staging; one rolled gather loop, the element selected by a uniform compare)
 #pragma unroll 1
-        for (int n = tid; n < N; n += kV2Threads) {
-          const long long idx = reflect_index(start + n, L);
-          edge_raw[n] = make_float2(__ldg(xt + idx), __ldg(xe + idx));
-        }
-        __syncthreads();
+          for (int r = 0; r < 16; ++r) {
+            const long long idx = reflect_index(start + tid + 128 * r, L);
+            const double w = __ldg(P.win_half + tid + 128 * r);
+            const cd val{w * (double)__ldg(xt + idx), w * (double)__ldg(xe + idx)};
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const double w = __ldg(P.win_half + tid + 128 * r);
-          const float2 x = edge_raw[tid + 128 * r];
-          v[r] = cd{w * (double)x.x, w * (double)x.y};
+            for (int rr = 0; rr < 16; ++rr)
+              if (rr == r) v[rr] = val;
+          }
+          __syncthreads();
+        } else {
+#pragma unroll 1
+          for (int n = tid; n < N; n += kV2Threads) {
+            const long long idx = reflect_index(start + n, L);
+            edge_raw[n] = make_float2(__ldg(xt + idx), (float)__ldg(xe + idx));
+          }
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const double w = __ldg(P.win_half + tid + 128 * r);
+            const float2 x = edge_raw[tid + 128 * r];
+            v[r] = cd{w * (double)x.x, w * (double)x.y};
+          }
         }
       }
       bfly16<false>(v);
@@ -297,7 +325,10 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
           const long long noff = offsets[np];
           const long long nL = offsets[np + 1] - noff;
           const long long nstart = (long long)(nxt_item - item_start[np]) * chunk * hop - N / 2 + (long long)(tid & 63) * 32;
-          if (nstart >= 0 && nstart < nL) prefetch_l1((tid < 64 ? tgt : est) + noff + nstart);
+          if (nstart >= 0 && nstart < nL) {
+            if (tid < 64) prefetch_l1(tgt + noff + nstart);
+            else prefetch_l1(est + noff + nstart);
+          }
         }
       }
 #endif
@@ -330,7 +361,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       bfly8<false>(a);
       bfly8<false>(b);
       // ---- epilogue, from registers
-      float lsd_acc = 0.f;
+      LT lsd_acc = 0;
       float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
       float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
       auto emit = [&](int k, cd zk, cd zn) {
@@ -340,8 +371,34 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
         // inside the differences that already exist between numpy's hypotf / torch's log10 and any
         // other libm (SSR_EXACT_F32_EPILOGUE switches to the IEEE-rounded forms for A/B tests).
         const float tre = (float)(zk.x + zn.x), tim = (float)(zk.y - zn.y);
-        const float ere = (float)(zk.y + zn.y), eim = (float)(zn.x - zk.x);
         const float tx = tre * tre + tim * tim;  // |T|^2
+        if (E64) {  // float64 estimate: the arithmetic of k1_generic.cuh's E64 branch
+          const float mt = sqrtf(tx);
+          const double me = hypot(zk.y + zn.y, zn.x - zk.x);  // np.abs(complex128)
+          if (st) {
+            row_t[k + (k >> 4)] = mt;
+            row_e[k + (k >> 4)] = (float)me;
+          }
+          if (want_lsd) {
+            const double den = me + 1e-12;
+            const double l = log10((double)(mt * mt) / (den * den) + 1e-12);  // target ** 2 is float32
+            lsd_acc += l * l;
+          }
+          if (want_lin) {
+            const double dt = (double)mt;
+            s_et = fma(me, dt, s_et);
+            s_tt = fma(dt, dt, s_tt);
+            s_ee = fma(me, me, s_ee);
+          }
+          if (want_log) {
+            const double le = log10(me + 1e-12), lt = (double)log10f(mt + 1e-12f);
+            l_et = fma(le, lt, l_et);
+            l_tt = fma(lt, lt, l_tt);
+            l_ee = fma(le, le, l_ee);
+          }
+          return;
+        }
+        const float ere = (float)(zk.y + zn.y), eim = (float)(zn.x - zk.x);
         const float ey = ere * ere + eim * eim;  // |E|^2
 #ifdef SSR_EXACT_F32_EPILOGUE
         const float mt = sqrtf(tx), me = sqrtf(ey);
@@ -388,7 +445,7 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
       }
       if (special) emit(1024, a[4], a[4]);
       if (want_lsd) {
-        const float w = warp_sum(lsd_acc);
+        const LT w = warp_sum(lsd_acc);
         if (lane == 0) lsd_part[fi][warp] = w;
       }
       pend_t = st;  // copied out after the next barrier (next frame's pass 1, or the item epilogue)
@@ -405,10 +462,11 @@ k_stft_metrics_2048(StftDev P, const float* __restrict__ est, const float* __res
     // ---- per-item reduction -> partials[item][0..7]
     double lsd_sum = 0.0;
     if (want_lsd && tid < nf) {
-      float sacc = 0.f;
+      LT sacc = 0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) sacc += lsd_part[tid][w];
-      lsd_sum = (double)sqrtf(sacc / (float)F);  // torch.mean(dim=3) ** 0.5 in float32
+      // torch.mean(dim=3) ** 0.5 in float32 (float64 when the estimate is float64)
+      lsd_sum = E64 ? sqrt((double)sacc / (double)F) : (double)sqrtf((float)sacc / (float)F);
     }
     double vals[7] = {lsd_sum, s_et, s_tt, s_ee, l_et, l_tt, l_ee};
     // only the sums the compile-time metric set fills are reduced (LSD-only: 1 of 7; the others stay 0)

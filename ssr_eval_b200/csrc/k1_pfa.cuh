@@ -22,9 +22,12 @@ namespace ssr {
 // left beside the CTAs' shared memory, so every table load is an L2 round trip that has to be hidden in
 // software.  Measured (LSD only, 256 pairs x 5 s): 21.6k pairs/s (3 CTAs, loads in place) -> 25.7k (2 CTAs,
 // 255 registers, constants in registers, software pipeline) -> 31.2k (3 CTAs, constants in TMEM, pipeline).
-template <int NQ, int FIXED>
+// ET = double: the ESTIMATE is a float64 waveform (the reference's IIR low-pass keys, see k1_generic.cuh): E stays
+// float64 from the waveform to the sums -- np.abs(complex128), float64 log10 / products -- only T is rounded to
+// complex64 / float32; same arithmetic as the generic kernel's float64-estimate path, 4x its speed.
+template <int NQ, int FIXED, typename ET = float>
 __global__ void __launch_bounds__(kV2Threads, 3)
-k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restrict__ tgt,
+k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict__ tgt,
                    const long long* __restrict__ offsets, const int* __restrict__ item_start,
                    const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,
                    double* __restrict__ partials, float* __restrict__ spec_e,
@@ -37,7 +40,9 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
   cd* const Yx = reinterpret_cast<cd*>(smem_raw + sizeof(cd) * (M + M / 8));
   __shared__ __align__(16) cd tw2[15 * 8];
   __shared__ __align__(16) cd wr_s[16];
-  __shared__ float lsd_part[kMaxChunk][NW];
+  constexpr bool E64 = sizeof(ET) == 8;
+  using LT = typename std::conditional<E64, double, float>::type;  // type of the per-frame LSD sums
+  __shared__ LT lsd_part[kMaxChunk][NW];
   __shared__ double red[NW][kPartials];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -142,12 +147,13 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
     const long long T = stft_frames(L, N, hop);
     const long long f0 = (long long)c * chunk;
     const int nf = (int)min((long long)chunk, T - f0);
-    const float* xe = est + off;
+    const ET* xe = est + off;
     const float* xt = tgt + off;
     double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
 
     // inputs of sub-transform (f, r): samples of both signals and window*chirp, NQ per thread
-    float ptx[NQ], pex[NQ];
+    float ptx[NQ];
+    ET pex[NQ];
     cd pcw[NQ];
     auto fetch_inputs = [&](long long f, int r) {
       const long long start = f * hop - N / 2;
@@ -156,7 +162,7 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
       for (int q = 0; q < NQ; ++q) {
         const int n = tid + 128 * q;
         ptx[q] = 0.f;
-        pex[q] = 0.f;
+        pex[q] = (ET)0;
         pcw[q] = cd{0.0, 0.0};
         if (n < P) {
           const long long si = start + (long long)R * n + r;
@@ -268,15 +274,39 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
       }
       __syncthreads();
       // ---- epilogue over the F bins (recombination on the fly)
-      float lsd_acc = 0.f;
+      LT lsd_acc = 0;
       float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
       float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
       for (int k = tid; k < F; k += kV2Threads) {
         const cd zk = combine(k);
         const cd zn = combine(k ? N - k : 0);
         const float tre = (float)(zk.x + zn.x), tim = (float)(zk.y - zn.y);
-        const float ere = (float)(zk.y + zn.y), eim = (float)(zn.x - zk.x);
         const float tx = tre * tre + tim * tim;
+        if (E64) {  // float64 estimate: the arithmetic of k1_generic.cuh's E64 branch
+          const float mt = sqrtf(tx);
+          const double me = hypot(zk.y + zn.y, zn.x - zk.x);  // np.abs(complex128)
+          if (st) st[k] = mt;
+          if (se) se[k] = (float)me;
+          if (want_lsd) {
+            const double den = me + 1e-12;
+            const double l = log10((double)(mt * mt) / (den * den) + 1e-12);  // target ** 2 is float32
+            lsd_acc += l * l;
+          }
+          if (want_lin) {
+            const double dt = (double)mt;
+            s_et = fma(me, dt, s_et);
+            s_tt = fma(dt, dt, s_tt);
+            s_ee = fma(me, me, s_ee);
+          }
+          if (want_log) {
+            const double le = log10(me + 1e-12), lt = (double)log10f(mt + 1e-12f);
+            l_et = fma(le, lt, l_et);
+            l_tt = fma(lt, lt, l_tt);
+            l_ee = fma(le, le, l_ee);
+          }
+          continue;
+        }
+        const float ere = (float)(zk.y + zn.y), eim = (float)(zn.x - zk.x);
         const float ey = ere * ere + eim * eim;
         const float me = __fsqrt_approx(ey);
         const float mt = (st || want_lin || want_log) ? __fsqrt_approx(tx) : 0.f;
@@ -301,17 +331,18 @@ k_stft_metrics_pfa(PfaDev D, const float* __restrict__ est, const float* __restr
         }
       }
       if (want_lsd) {
-        const float w = warp_sum(lsd_acc);
+        const LT w = warp_sum(lsd_acc);
         if (lane == 0) lsd_part[fi][warp] = w;
       }
     }
     __syncthreads();
     double lsd_sum = 0.0;
     if (want_lsd && tid < nf) {
-      float sacc = 0.f;
+      LT sacc = 0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) sacc += lsd_part[tid][w];
-      lsd_sum = (double)sqrtf(sacc / (float)F);
+      // torch.mean(dim=3) ** 0.5 in float32 (float64 when the estimate is float64)
+      lsd_sum = E64 ? sqrt((double)sacc / (double)F) : (double)sqrtf((float)sacc / (float)F);
     }
     double vals[7] = {lsd_sum, s_et, s_tt, s_ee, l_et, l_tt, l_ee};
 #pragma unroll

@@ -209,6 +209,45 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     return dispatch_k1<false, double, double>(plan, grid, smem, st, est64, tgt64, offs_dev, item_start, item_pair,
                                               w.n_items, w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
   }
+  if (est64 && plan->pfa && !force_generic_k1()) {
+    // float64 estimate on the PFA kernel (n_fft = R * P, e.g. 2229 at 48 kHz): same arithmetic as the generic kernel's
+    // float64-estimate path at ~4x its speed -- the IIR low-pass keys of setting_lowpass_filtering all come this way
+    const size_t smem_p = sizeof(cd) * (2048 + 256) + sizeof(cd) * (size_t)(plan->n_fft - plan->pdev.P);
+    int gp = sms * 3;
+    if (gp > w.n_items) gp = w.n_items;
+    const int nq = (plan->pdev.P + 127) / 128;
+#define SSR_PFA64_LAUNCH(NQ_)                                                                        \
+  do {                                                                                               \
+    auto kern = k_stft_metrics_pfa<NQ_, -1, double>;                                                 \
+    SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
+    kern<<<gp, kV2Threads, smem_p, st>>>(plan->pdev, est64, tgt, offs_dev, item_start, item_pair, w.n_items, \
+                                         w.chunk, flags, partials, spec_e, spec_t, spec_off, item_start + n + 1); \
+  } while (0)
+    if (nq <= 6) SSR_PFA64_LAUNCH(6);
+    else SSR_PFA64_LAUNCH(8);
+#undef SSR_PFA64_LAUNCH
+    SSR_LAUNCH_CHECK("k_stft_metrics_pfa<double>");
+    return SSR_OK;
+  }
+  if (est64 && !plan->bluestein && plan->logM == 11 && !force_generic_k1()) {
+    // float64 estimate on the 2048-point kernel (evaluation at 44.1 kHz and BASELINE cfg 2 sizes)
+    int g2 = sms * 4;
+    if (g2 > w.n_items) g2 = w.n_items;
+    const size_t smem2 = sizeof(cd) * (2048 + 256) + sizeof(float) * 2 * 1104;
+    if (plan->hop == 512) {
+      auto kern = k_stft_metrics_2048<-1, true, double>;
+      SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      kern<<<g2, kV2Threads, smem2, st>>>(plan->dev, est64, tgt, offs_dev, item_start, item_pair, w.n_items, w.chunk,
+                                          flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
+    } else {
+      auto kern = k_stft_metrics_2048<-1, false, double>;
+      SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      kern<<<g2, kV2Threads, smem2, st>>>(plan->dev, est64, tgt, offs_dev, item_start, item_pair, w.n_items, w.chunk,
+                                          flags, partials, spec_e, spec_t, spec_off, item_start + n + 1);
+    }
+    SSR_LAUNCH_CHECK("k_stft_metrics_2048<double>");
+    return SSR_OK;
+  }
   if (est64) {
     if (plan->bluestein)
       return dispatch_k1<true, double, float>(plan, grid, smem, st, est64, tgt, offs_dev, item_start, item_pair,

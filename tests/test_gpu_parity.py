@@ -127,6 +127,25 @@ def test_specialised_and_generic_k1_kernels_agree(n_fft, hop):
     assert np.abs(a - b).max() < 1e-6, (a, b)
 
 
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (2048, 441), (2229, 480), (743, 160)])
+def test_float64_estimates_on_the_specialised_kernels_agree_with_the_generic_one(n_fft, hop):
+    """A float64 estimate (the IIR low-pass keys) runs on k_stft_metrics_2048<.., double> / k_stft_metrics_pfa<.., double>;
+    the generic kernel's float64-estimate path (forced through SSR_FORCE_GENERIC_K1) must give the same metrics, and
+    both the oracle's (checked in test_float64_estimates_follow_the_reference_promotion)."""
+    code = (
+        "import sys, json, numpy as np; sys.path.insert(0, %r)\n"
+        "import oracle\n"
+        "from ssr_eval_b200.engine import StftMetrics\n"
+        "from ssr_eval_b200.synth import speech_like\n"
+        "t = speech_like(30000, 48000, seed=6); e = oracle.lowpass(t, 6000, 48000, order=8, _type='butter')\n"
+        "assert e.dtype == np.float64\n"
+        "print(json.dumps(StftMetrics(%d, %d).metrics([e, e[:9000], t[:2500].astype(np.float64)], [t, t[:9000], e[:2500].astype(np.float32)]).tolist()))\n"
+    ) % (_ROOT, n_fft, hop)
+    a, b = _run_forced(code, "SSR_FORCE_GENERIC_K1")
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.isfinite(a[:, :3]).all()   # (third pair: < 7 frames, SSIM NaN)
+    assert np.abs(np.nan_to_num(a) - np.nan_to_num(b)).max() < 1e-6, (a, b)
+
+
 def test_specialised_and_generic_k4_kernels_agree():
     code = (
         "import sys, json, numpy as np; sys.path.insert(0, %r)\n"

@@ -71,6 +71,19 @@ def main():
             ms = timeit(lambda: eng.metrics_device(est, tgt, off, flags, offsets_dev=off_d, out=out))
             report(name, ms, n, "pairs", n * (8 * L + 32))
         del tgt, est
+    if "k1_f64est" in which:
+        # float64 estimates (what the IIR low-pass keys of setting_lowpass_filtering hand to the metrics): generic kernel
+        for n_fft, hop, L, n in ((2048, 441, 220500, 256), (2229, 480, 240000, 128)):
+            tgt = 0.1 * torch.randn(n * L, generator=g, device=dev)
+            est = (tgt + 1e-3 * torch.randn(n * L, generator=g, device=dev)).double()
+            off = offsets_of([L] * n)
+            off_d = torch.from_numpy(off).to(dev)
+            eng = StftMetrics(n_fft, hop)
+            out = torch.empty((n, 4), dtype=torch.float64, device=dev)
+            for flags, name in ((1, "LSD"), (15, "all four")):
+                ms = timeit(lambda: eng.metrics_device(est, tgt, off, flags, offsets_dev=off_d, out=out), iters=2, warm=1)
+                report("K1 float64-estimate %d/%d %s" % (n_fft, hop, name), ms, n, "pairs", n * (12 * L + 32))
+            del tgt, est
     if "k0" in which:
         n = 1024 * 240000 * 2
         pcm = torch.randint(-32768, 32767, (n,), dtype=torch.int16, device=dev)
