@@ -34,7 +34,8 @@ __device__ __forceinline__ double ldg_pinned(const double* p) { return ldg_f64_p
 //           as the previous frame's shifted by 4, so they are kept -- already converted to float64 --
 //           in a 64-column TMEM ring; an interior frame loads only its 4 new samples per signal from
 //           global memory (one frame ahead, into 8 registers) and converts 8 instead of 32 values;
-//   pass 2: twiddles W_128^{jq} (120 values) from a conflict-free shared table;
+//   pass 2: twiddles W_128^{jq} (120 values) from a conflict-free shared table (RING) or, when there is no sample
+//           ring, from the other half of the CTA's tensor-memory columns;
 //   pass 3: no twiddles; every thread transforms a butterfly AND its Hermitian partner
 //           (k1_map.cuh), so Z[k] and Z[N-k] meet in registers and the epilogue needs no
 //           further shared-memory traffic.
@@ -56,7 +57,11 @@ k_stft_metrics_2048(StftDev P, const ET* __restrict__ est, const float* __restri
                     double* __restrict__ partials, float* __restrict__ spec_e,
                     float* __restrict__ spec_t, const long long* __restrict__ spec_off, int* __restrict__ next_item) {
   constexpr int N = 2048, F = 1025, NW = kV2Threads / 32;
-  constexpr int kTmemCols = RING ? 128 : 64;  // [0, 60) twiddles, [64, 128) sample ring
+  // tensor-memory columns of the CTA: [0, 60) the pass-1 twiddles; [64, 128): RING -- the float64 sample ring;
+  // otherwise (SSR_K1_TW2_TMEM) the 15 pass-2 twiddles W_128^{j2 q} of the thread, stored group by group
+  // (q0, q0+4, q0+8, q0+12): no shared-memory loads for them (240 of a frame's ~1480 LSU wavefronts)
+  constexpr bool kTw2Tmem = !RING;  // (hop 441: +3.4 %; for hop 512 the sample ring is the better use, +1 %)
+  constexpr int kTmemCols = (RING || kTw2Tmem) ? 128 : 64;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* const buf = reinterpret_cast<cd*>(smem_raw);                                // N + N/8 slots
   float2* const edge_raw = reinterpret_cast<float2*>(smem_raw);  // edge frames stage N raw pairs inside buf
@@ -92,6 +97,20 @@ k_stft_metrics_2048(StftDev P, const ET* __restrict__ est, const float* __restri
     unsigned r[16];
     tmem_pack4(w4, r);
     tmem_st16(tmem_base + 16 * c, r);
+  }
+  if (kTw2Tmem) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      cd w4[4];
+#pragma unroll
+      for (int q1 = 0; q1 < 4; ++q1) {
+        const int q = g + 4 * q1;
+        w4[q1] = P.tw[(16 * (tid & 7) * q) & 2047];  // W_128^{j2 q} (q = 0: 1, unused)
+      }
+      unsigned r[16];
+      tmem_pack4(w4, r);
+      tmem_st16(tmem_base + 64 + 16 * g, r);
+    }
   }
   tmem_wait_st();
   if (tid < 120) tw2[tid] = P.tw[16 * (tid & 7) * ((tid >> 3) + 1)];  // tw2[(q-1)*8 + j] = W_128^{jq}
@@ -343,7 +362,25 @@ k_stft_metrics_2048(StftDev P, const ET* __restrict__ est, const float* __restri
 #else
       // last radix-4 stage group by group with the twiddles of the next group fetched ahead (fft_core.cuh)
       bfly16_first<false>(v);
-      bfly16_second_twiddled<8>(v, t2, [&](int q, cd val) { b2[9 * q] = val; });
+      if (kTw2Tmem) {
+        unsigned r[2][16];
+        tmem_ld16(tmem_base + 64, r[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          tmem_wait_ld(r[g & 1]);
+          if (g < 3) tmem_ld16(tmem_base + 64 + 16 * (g + 1), r[(g + 1) & 1]);
+          cd w4[4];
+          tmem_unpack4(r[g & 1], w4);
+          bfly4<false>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+#pragma unroll
+          for (int q1 = 0; q1 < 4; ++q1) {
+            const int q = g + 4 * q1;
+            b2[9 * q] = q > 0 ? cmul(v[4 * g + q1], w4[q1]) : v[0];
+          }
+        }
+      } else {
+        bfly16_second_twiddled<8>(v, t2, [&](int q, cd val) { b2[9 * q] = val; });
+      }
 #endif
 #ifdef SSR_WARPLOCAL
       __syncwarp();
