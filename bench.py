@@ -367,10 +367,20 @@ def run_gpu(args):
             torch.cuda.synchronize()
             return n_pairs * iters / (a.elapsed_time(b) * 1e-3)
         eng48 = StftMetrics(2229, 480)
-        extras = {"unit": UNIT, "note": "device-resident, same batch; context only",
-                  "n_fft2048_hop512_all_four_metrics": rate(eng, N.METRIC_ALL, 5),
-                  "n_fft2229_hop480_lsd": rate(eng48, N.METRIC_LSD, 2),
-                  "n_fft2229_hop480_all_four_metrics": rate(eng48, N.METRIC_ALL, 2)}
+        peak_h = 6650.0
+        try:
+            peak_h = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+
+        def entry(pairs_per_s):  # same algorithmic bytes per pair as the contract metric
+            gbs = pairs_per_s * algorithmic_bytes(1, LENGTH) / 1e9
+            return {"pairs_per_s": pairs_per_s, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak_h}
+        extras = {"unit": UNIT, "note": "device-resident, same batch; context only (the reference's per-pair call computes "
+                                        "all four metrics; at 48 kHz its STFT is n_fft 2229 / hop 480, metrics.py:18-19)",
+                  "n_fft2048_hop512_all_four_metrics": entry(rate(eng, N.METRIC_ALL, 5)),
+                  "n_fft2229_hop480_lsd": entry(rate(eng48, N.METRIC_LSD, 2)),
+                  "n_fft2229_hop480_all_four_metrics": entry(rate(eng48, N.METRIC_ALL, 2))}
         del eng48
 
     check = {"mean_lsd": lsd_mean}
@@ -408,6 +418,20 @@ def run_gpu(args):
                     "kernel_share_of_step": k1_ms / ms if ms else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                     "note": "float64 FFT: the FP64 pipe binds, not HBM (see DESIGN.md roofline section)"}
+        # secondary roofline: the pipe that actually binds.  K1's hot loop issues 595 FP64 instructions per thread and
+        # frame (376 DADD + 111 DMUL + 108 DFMA, execution counts of the ncu source page, profiles/r02_ncu_summary.md),
+        # 128 threads per frame; the peak is measured in this run (DFMA chains, ssr_probe_fp64_rate)
+        roofline_fp64 = None
+        try:
+            fp64_peak = N.probe_fp64_rate(None)
+            frames = 1 + LENGTH // HOP
+            fp64_instr = 595.0 * 128.0 * frames * n_pairs
+            ach = fp64_instr / (k1_avg_ms * 1e-3)
+            roofline_fp64 = {"bound": "fp64_pipe", "achieved": ach / 1e9, "peak": fp64_peak / 1e9, "unit": "G thread-instr/s",
+                             "frac": ach / fp64_peak, "fp64_instr_per_thread_per_frame": 595,
+                             "peak_source": "measured in this run (ssr_probe_fp64_rate: 8 independent DFMA chains per thread)"}
+        except Exception as ex:  # the probe is measurement support only
+            roofline_fp64 = {"error": str(ex)}
         traffic_file = os.path.join(ROOT, "profiles", "k1_traffic_bytes.json")
         if os.path.exists(traffic_file):
             try:
@@ -443,6 +467,7 @@ def run_gpu(args):
                              "d2h_bytes_per_step": int(n_pairs * 4 * 8), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_fp64": roofline_fp64,
             "cpu_baseline": cpu,
             "check": check,
             "extras": extras,

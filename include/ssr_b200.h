@@ -214,6 +214,10 @@ int ssr_sosfiltfilt_batched(const double* sos_host, int n_sections, const double
  * ------------------------------------------------------------------------------------------ */
 int ssr_pcm16_to_float(const int16_t* src_dev, float* dst_dev, int64_t n, void* stream);
 
+/* Measurement support: the measured FP64 instruction rate of the current device (thread-instructions / s, DFMA chains),
+ * the denominator of bench.py's secondary (FP64-pipe) roofline for K1.  Synchronises the stream. */
+int ssr_probe_fp64_rate(double* thread_instr_per_s, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K8 ("next" row): the alignment step of the mp3 degradation,
  *   np.argmax(scipy.signal.correlate(decoded, x))            (ssr_eval/eval.py:319; the caller subtracts len(x), :319)

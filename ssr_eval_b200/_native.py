@@ -65,6 +65,7 @@ def lib():
     L.ssr_sosfiltfilt_workspace_bytes.restype = c_sz
     L.ssr_sosfiltfilt_batched.argtypes = [vp, c_int, vp, c_int, vp, vp, vp, c_int, vp, vp, c_sz, vp]
     L.ssr_pcm16_to_float.argtypes = [vp, vp, c_i64, vp]
+    L.ssr_probe_fp64_rate.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     L.ssr_lowpass_dense_plan_create.argtypes = [ctypes.POINTER(vp), c_int, c_int, vp, vp, vp, vp, vp]
     L.ssr_lowpass_dense_plan_destroy.argtypes = [vp]
     L.ssr_stft_hard_lowpass_dense_workspace_bytes.argtypes = [vp, vp, c_int]
@@ -94,6 +95,13 @@ def timing_collect():
     return ms.value, n.value
 
 
+def probe_fp64_rate(stream=None):
+    """Measured FP64 thread-instructions per second of the current device (see include/ssr_b200.h)."""
+    v = ctypes.c_double(0.0)
+    check(lib().ssr_probe_fp64_rate(ctypes.byref(v), stream), "ssr_probe_fp64_rate")
+    return v.value
+
+
 def launch_count():
     return int(lib().ssr_launch_count())
 
@@ -109,7 +117,7 @@ EXPORTED_SYMBOLS = (
     "ssr_lowpass_plan_create", "ssr_lowpass_plan_destroy", "ssr_stft_hard_lowpass_batched",
     "ssr_splice_plan_create", "ssr_splice_plan_destroy", "ssr_stft_splice_istft_batched",
     "ssr_sosfiltfilt_workspace_bytes", "ssr_sosfiltfilt_batched",
-    "ssr_pcm16_to_float",
+    "ssr_pcm16_to_float", "ssr_probe_fp64_rate",
     "ssr_lowpass_dense_plan_create", "ssr_lowpass_dense_plan_destroy",
     "ssr_stft_hard_lowpass_dense_workspace_bytes", "ssr_stft_hard_lowpass_dense_batched",
     "ssr_xcorr_workspace_bytes", "ssr_xcorr_argmax_batched",

@@ -39,9 +39,58 @@ __global__ void __launch_bounds__(256) k_pcm16_to_f32(const int16_t* __restrict_
   }
 }
 
+// FP64 pipe probe (measurement support for bench.py's secondary roofline): 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) k_probe_fp64(double* __restrict__ out, int iters, double a0) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = a0 + i + threadIdx.x;
+  const double b = 1.000000001, c = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fma(a[i], b, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keeps the chains alive, (practically) never stores
+}
+
 }  // namespace ssr
 
 using namespace ssr;
+
+/* Measured FP64 instruction rate of the device (thread-instructions per second, DFMA; DADD / DMUL run at the same
+ * rate on this part): the denominator of bench.py's FP64 roofline for K1, whose float64 FFT binds on that pipe. */
+extern "C" int ssr_probe_fp64_rate(double* thread_instr_per_s, void* stream) {
+  if (!thread_instr_per_s) return fail(SSR_ERR_INVALID, "ssr_probe_fp64_rate: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int sms = sm_count(), grid = sms * 8, iters = 4096;
+  double* scratch = nullptr;
+  SSR_CUDA_TRY(cudaMalloc(&scratch, sizeof(double) * (size_t)grid * 256));
+  cudaEvent_t e0, e1;
+  SSR_CUDA_TRY(cudaEventCreate(&e0));
+  SSR_CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+    cudaEventRecord(e0, st);
+    k_probe_fp64<<<grid, 256, 0, st>>>(scratch, iters, 1.0);
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) {
+      cudaFree(scratch);
+      return fail(SSR_ERR_CUDA, std::string("ssr_probe_fp64_rate: ") + cudaGetErrorString(e));
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  launch_counter().fetch_add(4, std::memory_order_relaxed);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(scratch);
+  *thread_instr_per_s = (double)grid * 256.0 * 8.0 * iters / (best * 1e-3);
+  return SSR_OK;
+}
 
 extern "C" int ssr_pcm16_to_float(const int16_t* src_dev, float* dst_dev, int64_t n, void* stream) {
   if (n < 0 || (n > 0 && (!src_dev || !dst_dev))) return fail(SSR_ERR_INVALID, "ssr_pcm16_to_float: bad argument");
