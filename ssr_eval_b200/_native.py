@@ -5,7 +5,9 @@ There is NO CPU fallback: if the shared library is missing or a call fails, this
 import ctypes
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libssr_b200.so")
+# SSR_B200_LIB: another build of the same library (A/B timing of kernel variants, tools/); default = the in-tree build
+_LIB_PATH = os.environ.get("SSR_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                          "libssr_b200.so")
 _lib = None
 
 SSR_OK = 0

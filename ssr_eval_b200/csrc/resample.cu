@@ -15,15 +15,38 @@
 #include <vector>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 
 struct ssr_resample_plan {
   int up, down, n_taps, half_len, n_pre_pad, n_pre_remove, K, device;
   int floor_len;  // 1: explicit-bank plan (resampy semantics): floor(n_in * up / down) outputs instead of ceil
   int is_f64;   // 1: float64 plan (bank holds doubles), for float64 waveforms
   void* bank;   // [up][K]: bank[phase*K + k] = h[phase + k*up] (0 beyond n_taps); float or double
+  // Copies of a float bank for the staged kernels, TRANSPOSED and in OUTPUT order: column n holds the phase of the
+  // outputs j = n (mod up), phase(n) = (half_len + n * down) % up, so that the threads of a warp (consecutive outputs)
+  // fetch their taps from consecutive addresses (ncu: with bank[phase][k] every tap load touched 32 lines), and with a
+  // FIXED row stride kBankStride so that the K loads of a thread are one base address + compile-time offsets.
+  //   bank_t[k * kBankStride + n] = bank[phase(n)][k]                                    (k_resample_bulk)
+  // k_resample_pair (pair_nl > 0) gets the two filters of the output pair (j, j + 1), j = n (mod up), already shifted
+  // onto its even-aligned window of 2 * pair_nl words, for both alignments par = 0 / 1 of the window's oldest sample:
+  //   pair_g[(par * 2 * pair_nl + q) * kBankStride + c] = (gA[2q], gA[2q+1]) for q < pair_nl, (gB[..]) for q >= pair_nl,
+  //   c = t % (up / gcd(up, 2)) for thread t of a CTA, n = (2 c) % up (consecutive threads -> consecutive columns),
+  //   gA[w] = bank[phase(n)][K - 1 + par - w], gB[w] = bank[phase(n + 1)][K - 1 + par + d(n) - w], 0 outside [0, K),
+  //   d(n) = (phase(n) + down) / up = how many samples the window of j + 1 starts after that of j
+  // and pair_thr[t] = {newest(jb + 2 t) - newest(jb), c(t)} for the threads t of a CTA (jb = the CTA's first
+  // output, a multiple of up, so neither depends on the CTA): no division in the kernel.
+  float* bank_t;
+  float2* pair_g;
+  int2* pair_thr;
+  int pair_nl, pair_tp, pair_m;  // 64-bit loads per window (0: no pair kernel), threads per CTA, 2 * pair_tp / up
 };
 
 namespace ssr {
+
+#ifndef SSR_K3_RP
+#define SSR_K3_RP 16  // output pairs per thread of k_resample_pair
+#endif
+constexpr int kBankStride = 512;  // row stride of the transposed banks (floats / float2s): up <= 512
 
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
@@ -178,7 +201,7 @@ template <int KMAX, int R, bool EXACT>
 __global__ void __launch_bounds__(512)
 k_resample_bulk(const float* __restrict__ x, const long long* __restrict__ in_off, float* __restrict__ y,
                 const long long* __restrict__ out_off, int u0, unsigned up, unsigned down, unsigned half_len, int K,
-                const float* __restrict__ bank, int span, long long x_total) {
+                const float* __restrict__ bank_t, int span, long long x_total) {
   extern __shared__ __align__(16) float xs_raw[];  // span + 8 floats (alignment slack of the bulk copy)
   __shared__ __align__(8) unsigned long long bar;
   const int u = u0 + blockIdx.y;
@@ -212,11 +235,11 @@ k_resample_bulk(const float* __restrict__ x, const long long* __restrict__ in_of
   const unsigned j0 = jb + threadIdx.x;
   const unsigned c0 = j0 * down + half_len;
   const unsigned i0 = c0 / up;
-  const unsigned phase = c0 - i0 * up;
+  const unsigned n0 = threadIdx.x % up;     // j0 % up (jb is a multiple of up): the row of bank_t with j0's phase
   const int p0 = (int)(i0 - ib) + (K - 1);  // index of the newest sample of output j0 inside xs
   float h[KMAX];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) h[k] = (EXACT || k < K) ? __ldg(bank + phase * K + k) : 0.f;
+  for (int k = 0; k < KMAX; ++k) h[k] = (EXACT || k < K) ? __ldg(bank_t + k * kBankStride + n0) : 0.f;
   const int step = (int)((TP / up) * down);  // input advance per TP outputs (TP % up == 0)
   if (bulk) mbar_wait(&bar, 0);
   else __syncthreads();
@@ -245,6 +268,98 @@ k_resample_bulk(const float* __restrict__ x, const long long* __restrict__ in_of
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_resample_pair: k_resample_bulk's successor for the production ratios.  ncu on k_resample_bulk: the LSU binds
+// (79 % of its wavefront peak) -- every tap of every output is one 4-byte LDS.  Here a thread produces the two
+// CONSECUTIVE outputs j, j+1, whose input windows overlap in all but d = 0 .. ceil(down / up) samples, from ONE set of
+// window loads, and those loads are 8-byte LDS.64: the window start is rounded down to an even shared-memory word
+// and the two filters are shifted to match ONCE per thread (taps outside [0, K) are zero), so the inner loop has no
+// data-dependent indexing.  Per output: 6 LDS.64 + 12 FMUL2 + 24 FADD against 21 LDS + 21 FMUL + 21 FADD.
+// The products of two neighbouring taps come from one packed FMUL2 (f32x2.cuh: each half rounded like the scalar
+// FMUL); the additions stay one scalar chain per output, oldest sample first -- scipy's order.  A zero tap adds
+// x * 0 = +-0 to an accumulator that started at +0 and can therefore never be -0: bit-identical for finite input.
+// Outputs j + m * 2 * TP (m = 0 .. RP-1) share j's phase (2 * TP % up == 0) and alignment (their windows are
+// `step` = (2 * TP / up) * down samples apart, even by choice of TP), so the shifted filters stay in registers.
+// Everything that depends on the thread alone comes from two host-built tables (ssr_resample_plan): the kernel has
+// no division and no range test; ncu on the first version showed half of its instructions in that prologue.
+// ---------------------------------------------------------------------------------------------
+template <int NL, int RP>
+__global__ void __launch_bounds__(512)
+k_resample_pair(const float* __restrict__ x, const long long* __restrict__ in_off, float* __restrict__ y,
+                const long long* __restrict__ out_off, int u0, int K, const float2* __restrict__ pair_g,
+                const int2* __restrict__ pair_thr, unsigned ib0, unsigned ib_step, int step, int span,
+                long long x_total) {
+  extern __shared__ __align__(16) float xs_raw[];  // span + 8 floats (alignment slack of the bulk copy)
+  __shared__ __align__(8) unsigned long long bar;
+  const int u = u0 + blockIdx.y;
+  const long long yoff = out_off[u];
+  const unsigned n_out = (unsigned)(out_off[u + 1] - yoff);
+  const unsigned TP = blockDim.x;
+  const unsigned jb = blockIdx.x * TP * (2 * RP);  // first output of this CTA (a multiple of up)
+  if (jb >= n_out) return;
+  const long long xoff = in_off[u];
+  const int n_in = (int)(in_off[u + 1] - xoff);
+  float* yu = y + yoff;
+  const unsigned ib = ib0 + blockIdx.x * ib_step;  // newest sample of the CTA's first output: (jb * down + half_len) / up
+  const int i_base = (int)ib - (K - 1);            // oldest sample the CTA touches (negative at the start)
+  const long long g0 = xoff + i_base;
+  const int shift = (int)(g0 & 3);
+  const int n_copy = (span + shift + 3) & ~3;
+  const bool bulk = i_base >= 0 && i_base + span <= n_in && g0 - shift + n_copy <= x_total;
+  const int sh = bulk ? shift : 0;  // sample i sits at xs_raw[i - i_base + sh]
+  if (bulk) {
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) bulk_load_1d(xs_raw, x + (g0 - shift), (unsigned)n_copy * 4u, &bar);
+  } else {
+    const float* xu = x + xoff;
+    for (int i = threadIdx.x; i < span; i += TP) {
+      const int gi = i_base + i;
+      xs_raw[i] = (gi >= 0 && gi < n_in) ? __ldg(xu + gi) : 0.f;
+    }
+  }
+  // the thread's output pair: window position and the two shifted filters (overlaps the copy)
+  const unsigned ja = jb + 2 * threadIdx.x;
+  const int2 tt = __ldg(pair_thr + threadIdx.x);  // {newest(ja) - ib, column of pair_g}
+  const int a_lo = tt.x + sh;                     // xs_raw index of the oldest sample of output ja
+  const int A0 = a_lo & ~1;                       // the even word at or below it: the window is xs_raw[A0 .. A0 + 2 NL)
+  float2 gA[NL], gB[NL];
+  {
+    const float2* g = pair_g + ((a_lo & 1) * (2 * NL) * kBankStride + tt.y);
+#pragma unroll
+    for (int n = 0; n < NL; ++n) {
+      gA[n] = __ldg(g + n * kBankStride);
+      gB[n] = __ldg(g + (NL + n) * kBankStride);
+    }
+  }
+  const bool st2 = (reinterpret_cast<uintptr_t>(yu) & 7) == 0;  // yu + ja is then 8-byte aligned (ja is even)
+  if (bulk) mbar_wait(&bar, 0);
+  else __syncthreads();
+#pragma unroll 2
+  for (int r = 0; r < RP; ++r) {
+    const float2* p = reinterpret_cast<const float2*>(xs_raw + A0 + r * step);
+    float accA = 0.f, accB = 0.f;
+#pragma unroll
+    for (int n = 0; n < NL; ++n) {
+      const float2 v = p[n];
+      const float2 pa = mul2(v, gA[n]), pb = mul2(v, gB[n]);
+      accA = __fadd_rn(__fadd_rn(accA, pa.x), pa.y);
+      accB = __fadd_rn(__fadd_rn(accB, pb.x), pb.y);
+    }
+    const unsigned j = ja + (unsigned)r * 2u * TP;
+    if (j + 1 < n_out) {
+      if (st2) *reinterpret_cast<float2*>(yu + j) = make_float2(accA, accB);
+      else {
+        yu[j] = accA;
+        yu[j + 1] = accB;
+      }
+    } else if (j < n_out) {
+      yu[j] = accA;
+    }
+  }
+}
+
 }  // namespace ssr
 
 using namespace ssr;
@@ -257,6 +372,88 @@ static bool force_old_k3() {
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
+}
+
+// SSR_FORCE_BULK_K3=1 skips k_resample_pair (A/B tests only)
+static bool force_bulk_k3() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_FORCE_BULK_K3");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// the transposed output-order copies of a float bank and k_resample_pair's tables (see ssr_resample_plan)
+static void free_staged_banks(ssr_resample_plan* p) {
+  if (p->bank_t) cudaFree(p->bank_t);
+  if (p->pair_g) cudaFree(p->pair_g);
+  if (p->pair_thr) cudaFree(p->pair_thr);
+  p->bank_t = nullptr;
+  p->pair_g = nullptr;
+  p->pair_thr = nullptr;
+}
+
+template <typename V>
+static cudaError_t upload(V** dst, const std::vector<V>& v) {
+  cudaError_t e = cudaMalloc(dst, v.size() * sizeof(V));
+  if (e == cudaSuccess) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice);
+  return e;
+}
+
+static cudaError_t make_staged_banks(ssr_resample_plan* p, const float* bank_host) {
+  p->bank_t = nullptr;
+  p->pair_g = nullptr;
+  p->pair_thr = nullptr;
+  p->pair_nl = p->pair_tp = p->pair_m = 0;
+  const int up = p->up, down = p->down, K = p->K;
+  if (up > kBankStride) return cudaSuccess;  // the staged kernels are not used for such plans
+  std::vector<int> phase(up);
+  for (int n = 0; n < up; ++n) phase[n] = (int)(((long long)p->half_len + (long long)n * down) % up);
+  std::vector<float> t((size_t)K * kBankStride, 0.f);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < up; ++n) t[(size_t)k * kBankStride + n] = bank_host[(size_t)phase[n] * K + k];
+  cudaError_t e = upload(&p->bank_t, t);
+  if (e != cudaSuccess) return e;
+  // k_resample_pair: instantiated for windows of 24 / 26 words (K = 21 / 22 of the evaluation's sample-rate pairs);
+  // block: 2 * TP = m * up outputs with m * down even (the window alignment repeats), smallest TP >= 192
+  const int d_max = (down + up - 1) / up;
+  const int NL = (K + d_max + 1 + 1) / 2;
+  if (NL != 12 && NL != 13) return cudaSuccess;
+  int m = 0;
+  for (int c = 1; (long long)c * up <= 1024; ++c)
+    if (((long long)c * up) % 2 == 0 && ((long long)c * down) % 2 == 0 && c * up / 2 >= 192) {
+      m = c;
+      break;
+    }
+  if (m == 0) return cudaSuccess;
+  const int TP = m * up / 2;
+  auto tap = [&](int ph, int k) { return (k >= 0 && k < K) ? bank_host[(size_t)ph * K + k] : 0.f; };
+  std::vector<float2> g((size_t)2 * 2 * NL * kBankStride, make_float2(0.f, 0.f));
+  const int P = (up % 2 == 0) ? up / 2 : up;  // distinct output pairs (mod up) a CTA's threads see
+  for (int par = 0; par < 2; ++par)
+    for (int c = 0; c < P; ++c) {
+      const int n = (2 * c) % up;
+      const int pa = phase[n], pb = phase[(n + 1) % up];
+      const int ka0 = K - 1 + par, kb0 = ka0 + (pa + down) / up;
+      for (int q = 0; q < NL; ++q) {
+        g[((size_t)par * 2 * NL + q) * kBankStride + c] = make_float2(tap(pa, ka0 - 2 * q), tap(pa, ka0 - 2 * q - 1));
+        g[((size_t)par * 2 * NL + NL + q) * kBankStride + c] =
+            make_float2(tap(pb, kb0 - 2 * q), tap(pb, kb0 - 2 * q - 1));
+      }
+    }
+  std::vector<int2> thr(TP);
+  for (int th = 0; th < TP; ++th) {
+    const long long c = (long long)p->half_len + 2LL * th * down;
+    thr[th] = make_int2((int)(c / up - p->half_len / up), th % P);
+  }
+  e = upload(&p->pair_g, g);
+  if (e == cudaSuccess) e = upload(&p->pair_thr, thr);
+  if (e != cudaSuccess) return e;
+  p->pair_nl = NL;
+  p->pair_tp = TP;
+  p->pair_m = m;
+  return cudaSuccess;
 }
 
 template <typename T>
@@ -286,7 +483,15 @@ static int resample_plan_create(ssr_resample_plan** out, int up, int down, const
   if (e == cudaSuccess) e = cudaMalloc(&p->bank, bank.size() * sizeof(T));
   if (e == cudaSuccess)
     e = cudaMemcpy(p->bank, bank.data(), bank.size() * sizeof(T), cudaMemcpyHostToDevice);
+  p->bank_t = nullptr;
+  p->pair_g = nullptr;
+  p->pair_thr = nullptr;
+  p->pair_nl = p->pair_tp = p->pair_m = 0;
+  if constexpr (sizeof(T) == 4) {
+    if (e == cudaSuccess) e = make_staged_banks(p, reinterpret_cast<const float*>(bank.data()));
+  }
   if (e != cudaSuccess) {
+    free_staged_banks(p);
     if (p->bank) cudaFree(p->bank);
     delete p;
     return fail(SSR_ERR_CUDA, std::string("resample plan upload: ") + cudaGetErrorString(e));
@@ -328,7 +533,13 @@ int ssr_resample_plan_create_bank(ssr_resample_plan** out, int up, int down, con
   cudaError_t e = cudaGetDevice(&p->device);
   if (e == cudaSuccess) e = cudaMalloc(&p->bank, sizeof(float) * (size_t)up * K);
   if (e == cudaSuccess) e = cudaMemcpy(p->bank, bank_host, sizeof(float) * (size_t)up * K, cudaMemcpyHostToDevice);
+  p->bank_t = nullptr;
+  p->pair_g = nullptr;
+  p->pair_thr = nullptr;
+  p->pair_nl = p->pair_tp = p->pair_m = 0;
+  if (e == cudaSuccess) e = make_staged_banks(p, bank_host);
   if (e != cudaSuccess) {
+    free_staged_banks(p);
     if (p->bank) cudaFree(p->bank);
     delete p;
     return fail(SSR_ERR_CUDA, std::string("resample bank plan upload: ") + cudaGetErrorString(e));
@@ -340,6 +551,7 @@ int ssr_resample_plan_create_bank(ssr_resample_plan** out, int up, int down, con
 int ssr_resample_plan_destroy(ssr_resample_plan* plan) {
   if (!plan) return SSR_OK;
   if (plan->bank) cudaFree(plan->bank);
+  free_staged_banks(plan);
   delete plan;
   return SSR_OK;
 }
@@ -403,6 +615,47 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
   }
   if (max_out == 0) return SSR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long max_in = 0;
+  for (int u = 0; u < n; ++u) max_in = std::max<long long>(max_in, in_offsets_host[u + 1] - in_offsets_host[u]);
+  {
+    // production path for the sample-rate pairs of the evaluation (K = 21 / 22): two consecutive outputs per thread
+    // (block size and tables: make_staged_banks)
+    constexpr int RP = SSR_K3_RP;
+    const int d_max = (plan->down + plan->up - 1) / plan->up;
+    const int NL = plan->pair_nl;  // 64-bit loads covering K + d_max samples at either alignment
+    const int TPP = plan->pair_tp;
+    const long long outs = 2LL * TPP * RP;
+    // samples the CTA's windows reach: newest(last) - newest(first) + K, + d_max, + the zero-tap overhang of a window
+    const long long spanp = (outs - 1) * plan->down / plan->up + 2 + plan->K + d_max + 2 * NL - plan->K + 2;
+    const long long c_max = (max_out + outs) * plan->down + plan->half_len;
+    if (NL > 0 && plan->pair_g && plan->pair_thr && (spanp + 8) * (long long)sizeof(float) <= 64 * 1024 &&
+        c_max < 0x7fffffffLL && max_in < 0x7fffffffLL && !force_old_k3() && !force_bulk_k3()) {
+      const int span = (int)spanp;
+      const size_t smem = sizeof(float) * (size_t)(span + 8);
+      const long long x_total = in_offsets_host[n];
+      const unsigned ib0 = (unsigned)(plan->half_len / plan->up);
+      const unsigned ib_step = (unsigned)(plan->pair_m * RP * plan->down);  // (2 TP RP / up) * down
+      const int step = plan->pair_m * plan->down;
+      for (int u0 = 0; u0 < n; u0 += 32768) {
+        int nu = n - u0 < 32768 ? n - u0 : 32768;
+        dim3 grid((unsigned)((max_out + outs - 1) / outs), nu);
+        const long long* io = reinterpret_cast<const long long*>(in_offsets_dev);
+        const long long* oo = reinterpret_cast<const long long*>(out_offsets_dev);
+#define SSR_K3P_LAUNCH(NLV)                                                                                      \
+  do {                                                                                                           \
+    auto kern = k_resample_pair<NLV, RP>;                                                                        \
+    SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    kern<<<grid, TPP, smem, st>>>(x_dev, io, y_dev, oo, u0, plan->K, plan->pair_g, plan->pair_thr, ib0, ib_step, \
+                                  step, span, x_total);                                                          \
+  } while (0)
+        if (NL == 12) SSR_K3P_LAUNCH(12);  // 44.1k -> 48k (160/147), 16k -> 44.1k (441/160), 8k / 12k / 24k -> 44.1k
+        else SSR_K3P_LAUNCH(13);           // 48k -> 44.1k (147/160)
+#undef SSR_K3P_LAUNCH
+        SSR_LAUNCH_CHECK("k_resample_pair");
+      }
+      return SSR_OK;
+    }
+  }
   // tiled kernels: block = smallest multiple of `up` that is >= 256 threads (<= 512)
   int TP = plan->up * ((256 + plan->up - 1) / plan->up);
   {
@@ -410,9 +663,7 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
     constexpr int R2 = 16;
     const long long span2 = ((long long)TP * R2 - 1) * plan->down / plan->up + 2 + plan->K;
     const long long c_max = (max_out + (long long)TP * R2) * plan->down + plan->half_len;
-    long long max_in = 0;
-    for (int u = 0; u < n; ++u) max_in = std::max<long long>(max_in, in_offsets_host[u + 1] - in_offsets_host[u]);
-    if (TP <= 512 && plan->K <= 48 && (span2 + 8) * (long long)sizeof(float) <= 64 * 1024 && c_max < 0x7fffffffLL &&
+    if (plan->bank_t && TP <= 512 && plan->K <= 48 && (span2 + 8) * (long long)sizeof(float) <= 64 * 1024 && c_max < 0x7fffffffLL &&
         max_in < 0x7fffffffLL && !force_old_k3()) {
       const int span = (int)span2;
       const size_t smem = sizeof(float) * (size_t)(span + 8);
@@ -427,8 +678,7 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
     auto kern = k_resample_bulk<KM, R2, EX>;                                                                     \
     SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
     kern<<<grid, TP, smem, st>>>(x_dev, io, y_dev, oo, u0, (unsigned)plan->up, (unsigned)plan->down,            \
-                                 (unsigned)plan->half_len, plan->K, static_cast<const float*>(plan->bank), span, \
-                                 x_total);                                                                       \
+                                 (unsigned)plan->half_len, plan->K, plan->bank_t, span, x_total);                \
   } while (0)
         if (plan->K == 21) SSR_K3B_LAUNCH(21, true);       // 44.1k <-> 48k up (160/147), 16k -> 44.1k (441/160)
         else if (plan->K == 22) SSR_K3B_LAUNCH(22, true);  // 48k -> 44.1k (147/160)
