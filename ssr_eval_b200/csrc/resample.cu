@@ -43,6 +43,12 @@ struct ssr_resample_plan {
 
 namespace ssr {
 
+#ifndef SSR_K3_MINB320
+#define SSR_K3_MINB320 3
+#endif
+#ifndef SSR_K3_MIN_TP
+#define SSR_K3_MIN_TP 128  // smallest CTA of k_resample_pair (measured: 160 threads x 5 CTAs per SM beat 320 x 3)
+#endif
 #ifndef SSR_K3_RP
 #define SSR_K3_RP 16  // output pairs per thread of k_resample_pair
 #endif
@@ -284,8 +290,8 @@ k_resample_bulk(const float* __restrict__ x, const long long* __restrict__ in_of
 // Everything that depends on the thread alone comes from two host-built tables (ssr_resample_plan): the kernel has
 // no division and no range test; ncu on the first version showed half of its instructions in that prologue.
 // ---------------------------------------------------------------------------------------------
-template <int NL, int RP>
-__global__ void __launch_bounds__(512)
+template <int NL, int RP, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_resample_pair(const float* __restrict__ x, const long long* __restrict__ in_off, float* __restrict__ y,
                 const long long* __restrict__ out_off, int u0, int K, const float2* __restrict__ pair_g,
                 const int2* __restrict__ pair_thr, unsigned ib0, unsigned ib_step, int step, int span,
@@ -336,6 +342,7 @@ k_resample_pair(const float* __restrict__ x, const long long* __restrict__ in_of
   const bool st2 = (reinterpret_cast<uintptr_t>(yu) & 7) == 0;  // yu + ja is then 8-byte aligned (ja is even)
   if (bulk) mbar_wait(&bar, 0);
   else __syncthreads();
+#ifdef SSR_K3_LOOP_OLD
 #pragma unroll 2
   for (int r = 0; r < RP; ++r) {
     const float2* p = reinterpret_cast<const float2*>(xs_raw + A0 + r * step);
@@ -347,6 +354,25 @@ k_resample_pair(const float* __restrict__ x, const long long* __restrict__ in_of
       accA = __fadd_rn(__fadd_rn(accA, pa.x), pa.y);
       accB = __fadd_rn(__fadd_rn(accB, pb.x), pb.y);
     }
+#else
+  const unsigned xs_addr = (unsigned)__cvta_generic_to_shared(xs_raw + A0);
+#pragma unroll 1
+  for (int r = 0; r < RP; ++r) {
+    // the whole window first (issued where written: the compiler otherwise serialises load -> 6 operations -> load
+    // through one register pair, every step waiting out the shared-memory latency), then the arithmetic
+    float2 v[NL];
+    const unsigned pa0 = xs_addr + (unsigned)(r * step) * 4u;
+#pragma unroll
+    for (int n = 0; n < NL; ++n)
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[n].x), "=f"(v[n].y) : "r"(pa0 + 8u * n));
+    float accA = 0.f, accB = 0.f;
+#pragma unroll
+    for (int n = 0; n < NL; ++n) {
+      const float2 pa = mul2(v[n], gA[n]), pb = mul2(v[n], gB[n]);
+      accA = __fadd_rn(__fadd_rn(accA, pa.x), pa.y);
+      accB = __fadd_rn(__fadd_rn(accB, pb.x), pb.y);
+    }
+#endif
     const unsigned j = ja + (unsigned)r * 2u * TP;
     if (j + 1 < n_out) {
       if (st2) *reinterpret_cast<float2*>(yu + j) = make_float2(accA, accB);
@@ -416,13 +442,13 @@ static cudaError_t make_staged_banks(ssr_resample_plan* p, const float* bank_hos
   cudaError_t e = upload(&p->bank_t, t);
   if (e != cudaSuccess) return e;
   // k_resample_pair: instantiated for windows of 24 / 26 words (K = 21 / 22 of the evaluation's sample-rate pairs);
-  // block: 2 * TP = m * up outputs with m * down even (the window alignment repeats), smallest TP >= 192
+  // block: 2 * TP = m * up outputs with m * down even (the window alignment repeats), smallest TP >= SSR_K3_MIN_TP
   const int d_max = (down + up - 1) / up;
   const int NL = (K + d_max + 1 + 1) / 2;
   if (NL != 12 && NL != 13) return cudaSuccess;
   int m = 0;
   for (int c = 1; (long long)c * up <= 1024; ++c)
-    if (((long long)c * up) % 2 == 0 && ((long long)c * down) % 2 == 0 && c * up / 2 >= 192) {
+    if (((long long)c * up) % 2 == 0 && ((long long)c * down) % 2 == 0 && c * up / 2 >= SSR_K3_MIN_TP) {
       m = c;
       break;
     }
@@ -641,15 +667,20 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
         dim3 grid((unsigned)((max_out + outs - 1) / outs), nu);
         const long long* io = reinterpret_cast<const long long*>(in_offsets_dev);
         const long long* oo = reinterpret_cast<const long long*>(out_offsets_dev);
-#define SSR_K3P_LAUNCH(NLV)                                                                                      \
+#define SSR_K3P_LAUNCH(NLV, MAXT, MINB)                                                                          \
   do {                                                                                                           \
-    auto kern = k_resample_pair<NLV, RP>;                                                                        \
+    auto kern = k_resample_pair<NLV, RP, MAXT, MINB>;                                                                      \
     SSR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
     kern<<<grid, TPP, smem, st>>>(x_dev, io, y_dev, oo, u0, plan->K, plan->pair_g, plan->pair_thr, ib0, ib_step, \
                                   step, span, x_total);                                                          \
   } while (0)
-        if (NL == 12) SSR_K3P_LAUNCH(12);  // 44.1k -> 48k (160/147), 16k -> 44.1k (441/160), 8k / 12k / 24k -> 44.1k
-        else SSR_K3P_LAUNCH(13);           // 48k -> 44.1k (147/160)
+        // register caps: the largest that keep MINB CTAs of MAXT threads on an SM (64 / 72 / 80 registers)
+        if (NL == 12 && TPP <= 160) SSR_K3P_LAUNCH(12, 160, 5);
+        else if (NL == 12 && TPP <= 320) SSR_K3P_LAUNCH(12, 320, SSR_K3_MINB320);  // 44.1k -> 48k (160/147)
+        else if (NL == 12) SSR_K3P_LAUNCH(12, 448, 2);                // 16k -> 44.1k (441/160), 8k / 12k / 24k -> 44.1k
+        else if (TPP <= 160) SSR_K3P_LAUNCH(13, 160, 5);              // 48k -> 44.1k (147/160)
+        else if (TPP <= 320) SSR_K3P_LAUNCH(13, 320, 2);              // 48k -> 44.1k (147/160)
+        else SSR_K3P_LAUNCH(13, 448, 2);
 #undef SSR_K3P_LAUNCH
         SSR_LAUNCH_CHECK("k_resample_pair");
       }

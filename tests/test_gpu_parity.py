@@ -297,11 +297,14 @@ def test_resample_poly_vs_scipy(up, down):
     print(f"resample {up}/{down}: {n_exact}/{len(waves)} utterances bit-exact vs scipy")
 
 
-@pytest.mark.parametrize("up,down", [(160, 147), (147, 160), (441, 160), (3, 2)])
+@pytest.mark.parametrize("up,down", [(160, 147), (147, 160), (441, 160), (441, 80), (147, 80), (3, 2)])
 def test_resample_bulk_staged_tiles_vs_scipy(up, down):
-    """Utterances long enough for interior tiles of k_resample_bulk (input span staged by ONE cp.async.bulk / TMA copy
+    """Utterances long enough for interior tiles of the staged kernels (input span staged by ONE cp.async.bulk / TMA copy
     from a 16-byte-aligned address below the span) next to edge tiles (element-wise staging with zero extension):
-    odd offsets inside the batch buffer exercise every alignment shift, the last utterance ends the buffer."""
+    odd offsets inside the batch buffer exercise every alignment shift (and both window alignments and the scalar /
+    8-byte store paths of k_resample_pair), the last utterance ends the buffer.  The sample-rate pairs of the evaluation
+    (K = 21 / 22 taps per phase) run k_resample_pair -- two outputs per thread, zero-padded shifted filters --, 3/2
+    runs k_resample_bulk: both must reproduce scipy's float32 result bit for bit."""
     from ssr_eval_b200.engine import PolyphaseResampler
     rs = PolyphaseResampler(up, down)
     lens = (50001, 3, 131071, 44100, 65538, 30001)
