@@ -164,6 +164,15 @@ k_stft_metrics_2048(StftDev P, const ET* __restrict__ est, const float* __restri
     double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
     float* pend_t = nullptr;
     float* pend_e = nullptr;
+    const SpecLayout sl = spec_layout(spec_e, spec_t, F);
+    auto copy_out = [&](int k) {  // one bin of the staged magnitude rows -> global (consecutive threads, consecutive bins)
+      if (sl.step == 2) {         // interleaved (estimate, target) pairs: one 8-byte store
+        reinterpret_cast<float2*>(pend_e)[k] = make_float2(row_e[k + (k >> 4)], row_t[k + (k >> 4)]);
+      } else {
+        pend_t[k] = row_t[k + (k >> 4)];
+        if (pend_e) pend_e[k] = row_e[k + (k >> 4)];
+      }
+    };
 
     long long ring_next = -1;  // RING: frame whose 12 older sample blocks sit in the tensor-memory ring
     float pre_t[4];  // RING: the frame's 4 new samples per signal
@@ -314,8 +323,7 @@ k_stft_metrics_2048(StftDev P, const ET* __restrict__ est, const float* __restri
       __syncthreads();
       if (pend_t) {  // coalesced copy-out of the previous frame's magnitude rows (all epilogues are done)
         for (int k = tid; k < F; k += kV2Threads) {
-          pend_t[k] = row_t[k + (k >> 4)];
-          if (pend_e) pend_e[k] = row_e[k + (k >> 4)];
+          copy_out(k);
         }
         pend_t = nullptr;
       }
@@ -399,8 +407,8 @@ k_stft_metrics_2048(StftDev P, const ET* __restrict__ est, const float* __restri
       bfly8<false>(b);
       // ---- epilogue, from registers
       LT lsd_acc = 0;
-      float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
-      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
+      float* st = spec_t ? spec_t + spec_off[p] + f * sl.pitch : nullptr;
+      float* se = spec_e ? spec_e + spec_off[p] + f * sl.pitch : nullptr;
       auto emit = [&](int k, cd zk, cd zn) {
         // T = (Z[k] + conj Z[N-k]) / 2,  E = (Z[k] - conj Z[N-k]) / (2i); the 1/2 is in the window.
         // complex64 rounding as librosa stores it, then float32 arithmetic as torch runs it; the
@@ -491,8 +499,7 @@ k_stft_metrics_2048(StftDev P, const ET* __restrict__ est, const float* __restri
     __syncthreads();
     if (pend_t) {
       for (int k = tid; k < F; k += kV2Threads) {
-        pend_t[k] = row_t[k + (k >> 4)];
-        if (pend_e) pend_e[k] = row_e[k + (k >> 4)];
+        copy_out(k);
       }
       pend_t = nullptr;
     }

@@ -80,11 +80,41 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 
 // ---------------------------------------------------------------------------------------------
+// Spectrogram layouts the K1 kernels write.  Plain: one (T, F) float image per signal, row pitch F (the magnitude
+// entry point).  Interleaved (K1 -> K2, spec_t == spec_e + 1): ONE image of (estimate, target) float2 pairs with an
+// even row pitch, so that every row starts on a 16-byte boundary and K2 streams it with 16-byte copies straight into
+// the (x, y)-pair layout its packed arithmetic works on.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int spec_pitch_pairs(int F) { return (F + 1) & ~1; }  // float2 per interleaved row
+struct SpecLayout {
+  int step;         // floats between consecutive bins of one signal (1 plain, 2 interleaved)
+  long long pitch;  // floats per row
+};
+__device__ __forceinline__ SpecLayout spec_layout(const float* spec_e, const float* spec_t, int F) {
+  const bool inter = spec_e != nullptr && spec_t == spec_e + 1;
+  SpecLayout l;
+  l.step = inter ? 2 : 1;
+  l.pitch = inter ? 2 * spec_pitch_pairs(F) : F;
+  return l;
+}
+
+// magnitudes of bin k of one frame -> the spectrogram row(s); st / se = row starts (null: not wanted)
+__device__ __forceinline__ void spec_store(const SpecLayout& l, float* st, float* se, int k, float mt, float me) {
+  if (l.step == 2) {
+    reinterpret_cast<float2*>(se)[k] = make_float2(me, mt);  // rows are 8-byte aligned (even pitch, even offsets)
+  } else {
+    if (st) st[k] = mt;
+    if (se) se[k] = me;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // setup: work-item table.  item_start[p] = first work item of pair p (item = chunk of <= `chunk`
-// consecutive frames), item_pair[item] = p, spec_off[p] = first spectrogram element of pair p.
+// consecutive frames), item_pair[item] = p, spec_off[p] = first spectrogram element (float) of pair p: frames before
+// it x spec_pitch, the floats per spectrogram row (SpecLayout below).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_setup(const long long* __restrict__ offsets, int n, int n_fft, int hop, int chunk,
-                        int F, int* __restrict__ item_start, int* __restrict__ item_pair,
+                        int spec_pitch, int* __restrict__ item_start, int* __restrict__ item_pair,
                         long long* __restrict__ spec_off) {
   __shared__ long long s_items[1024], s_frames[1024];
   const int t = threadIdx.x;
@@ -116,7 +146,7 @@ __global__ void k_setup(const long long* __restrict__ offsets, int n, int n_fft,
     long long T = stft_frames(offsets[p + 1] - offsets[p], n_fft, hop);
     int nc = (int)((T + chunk - 1) / chunk);
     item_start[p] = (int)it;
-    spec_off[p] = fr * F;
+    spec_off[p] = fr * spec_pitch;
     for (int c = 0; c < nc; ++c) item_pair[it + c] = p;
     it += nc;
     fr += T;
@@ -124,7 +154,7 @@ __global__ void k_setup(const long long* __restrict__ offsets, int n, int n_fft,
   if (hi == n) {
     item_start[n] = (int)it;
     item_start[n + 1] = 0;  // work-item counter of the persistent kernels (dynamic scheduling)
-    spec_off[n] = fr * F;
+    spec_off[n] = fr * spec_pitch;
   }
 }
 

@@ -41,6 +41,7 @@ k_stft_metrics(StftDev P, const ET* __restrict__ est, const TT* __restrict__ tgt
   const int N = P.n_fft, F = P.F, hop = P.hop;
   const bool want_lsd = flags & SSR_METRIC_LSD, want_log = flags & SSR_METRIC_LOG_SISPEC,
              want_lin = flags & SSR_METRIC_SISPEC;
+  const SpecLayout sl = spec_layout(spec_e, spec_t, F);
 
   __shared__ int item_slot;
   for (int item = next_work_item(next_item, &item_slot); item < n_items; item = next_work_item(next_item, &item_slot)) {
@@ -88,8 +89,8 @@ k_stft_metrics(StftDev P, const ET* __restrict__ est, const TT* __restrict__ tgt
       }
       // ---- epilogue over the F = n_fft/2+1 bins
       LT lsd_acc = 0;
-      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
-      float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
+      float* se = spec_e ? spec_e + spec_off[p] + f * sl.pitch : nullptr;
+      float* st = spec_t ? spec_t + spec_off[p] + f * sl.pitch : nullptr;
       for (int k = tid; k < F; k += kThreads) {
         cd a, b;
         if (!BLUE) {
@@ -106,8 +107,7 @@ k_stft_metrics(StftDev P, const ET* __restrict__ est, const TT* __restrict__ tgt
         if (E64) {
           const double me = hypot(a.y + b.y, b.x - a.x);  // np.abs(complex128)
           const double mt64 = T64 ? hypot(a.x + b.x, a.y - b.y) : (double)mt;
-          if (st) st[k] = T64 ? (float)mt64 : mt;
-          if (se) se[k] = (float)me;
+          spec_store(sl, st, se, k, T64 ? (float)mt64 : mt, (float)me);
           if (want_lsd) {
             const double den = me + 1e-12;
             // target ** 2 is float32 for a float32 target, float64 for a float64 one
@@ -130,8 +130,7 @@ k_stft_metrics(StftDev P, const ET* __restrict__ est, const TT* __restrict__ tgt
         }
         float ere = (float)(a.y + b.y), eim = (float)(b.x - a.x);
         float me = sqrtf(ere * ere + eim * eim);
-        if (st) st[k] = mt;
-        if (se) se[k] = me;
+        spec_store(sl, st, se, k, mt, me);
         if (want_lsd) {
           float den = me + 1e-12f;
           float q = (mt * mt) / (den * den) + 1e-12f;

@@ -54,6 +54,7 @@ k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict
     spec_e = nullptr;
     spec_t = nullptr;
   }
+  const SpecLayout sl = spec_layout(spec_e, spec_t, F);
 
   __shared__ unsigned tmem_slot;
   if (tid < 120) tw2[tid] = D.tw[16 * (tid & 7) * ((tid >> 3) + 1)];
@@ -275,8 +276,8 @@ k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict
       __syncthreads();
       // ---- epilogue over the F bins (recombination on the fly)
       LT lsd_acc = 0;
-      float* st = spec_t ? spec_t + spec_off[p] + f * F : nullptr;
-      float* se = spec_e ? spec_e + spec_off[p] + f * F : nullptr;
+      float* st = spec_t ? spec_t + spec_off[p] + f * sl.pitch : nullptr;
+      float* se = spec_e ? spec_e + spec_off[p] + f * sl.pitch : nullptr;
       for (int k = tid; k < F; k += kV2Threads) {
         const cd zk = combine(k);
         const cd zn = combine(k ? N - k : 0);
@@ -285,8 +286,7 @@ k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict
         if (E64) {  // float64 estimate: the arithmetic of k1_generic.cuh's E64 branch
           const float mt = sqrtf(tx);
           const double me = hypot(zk.y + zn.y, zn.x - zk.x);  // np.abs(complex128)
-          if (st) st[k] = mt;
-          if (se) se[k] = (float)me;
+          spec_store(sl, st, se, k, mt, (float)me);
           if (want_lsd) {
             const double den = me + 1e-12;
             const double l = log10((double)(mt * mt) / (den * den) + 1e-12);  // target ** 2 is float32
@@ -310,8 +310,7 @@ k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict
         const float ey = ere * ere + eim * eim;
         const float me = __fsqrt_approx(ey);
         const float mt = (st || want_lin || want_log) ? __fsqrt_approx(tx) : 0.f;
-        if (st) st[k] = mt;
-        if (se) se[k] = me;
+        spec_store(sl, st, se, k, mt, me);
         if (want_lsd) {
           const float den = me + 1e-12f;
           const float l = __log10f(__fdividef(tx, den * den) + 1e-12f);

@@ -5,6 +5,12 @@
 
 namespace ssr {
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: SSIM of two (T, F) float32 magnitude images, valid 7x7 windows only (skimage crops the
 // 3-pixel border, so the reflect boundary mode of uniform_filter never reaches the mean).
@@ -19,9 +25,9 @@ namespace ssr {
 constexpr int kSsimThreads = 128;
 
 __global__ void __launch_bounds__(kSsimThreads)
-k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
-       const long long* __restrict__ spec_off, const long long* __restrict__ offsets, int pair0,
-       int n_fft, int hop, int F, int tiles_x, int tiles_per_pair, double* __restrict__ ssim_part) {
+k_ssim(const float2* __restrict__ spec2, const long long* __restrict__ spec_off,
+       const long long* __restrict__ offsets, int pair0, int n_fft, int hop, int F, int tiles_x, int tiles_per_pair,
+       double* __restrict__ ssim_part) {
   const int p = pair0 + blockIdx.y;
   const int tile = blockIdx.x;
   const int ty = tile / tiles_x, tx = tile % tiles_x;
@@ -38,8 +44,8 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   const int t = threadIdx.x;
   const int c = 2 * t;  // first of this thread's two columns inside the tile
   const bool ok0 = (c0 + c) < cols_out, ok1 = (c0 + c + 1) < cols_out;
-  const float* E = spec_e + spec_off[p];
-  const float* G = spec_t + spec_off[p];
+  const int Fp = spec_pitch_pairs(F);                // row pitch of the interleaved image (float2; even)
+  const float2* img = spec2 + (spec_off[p] >> 1);    // spec_off counts floats
   // 7 stages = the unroll factor of the row loop: the stage a row lives in and the stage the next copy refills are
   // compile-time constants inside the unrolled body (no wrap-around arithmetic, selects or index registers)
   constexpr int RB = kSsimTC + 8, STAGES = 7;
@@ -72,40 +78,29 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
   const float C1 = 0.0004f, C2 = 0.0036f;  // (0.01*2)^2, (0.03*2)^2
   const float2 inv49_2 = make_float2(inv49, inv49), cov2 = make_float2(cov_norm, cov_norm);
 
-  // rows stream global -> shared with cp.async (LDGSTS), STAGES-1 rows in flight; columns beyond the
-  // image are zero-filled by the copy itself (src-size 0).  All per-row address arithmetic is kept in
-  // running pointers / counters (the copy engine work is 6 LDGSTS per thread and row).
-  int coff[3], cbytes[3];
-  unsigned sdst[3];
-#pragma unroll
-  for (int u = 0; u < 3; ++u) {
-    const int col = t + u * kSsimThreads;
-    const bool use = (u < 2 || t < 8);
-    const bool in = use && (c0 + col) < F;
-    coff[u] = in ? col : 0;
-    cbytes[u] = in ? 4 : 0;
-    sdst[u] = (unsigned)__cvta_generic_to_shared(&rowbuf[0][use ? col : 0]);
-  }
-  const float* e_next = E + (long long)r0 * F + c0;  // row to be issued next
-  const float* g_next = G + (long long)r0 * F + c0;
+  // rows stream global -> shared with 16-byte cp.async (LDGSTS.128), STAGES-1 rows in flight.  K1 writes the image
+  // as (estimate, target) pairs with an even row pitch, so a row of the tile is RB / 2 = 132 aligned 16-byte chunks that
+  // land directly in the pair layout: ONE copy per thread and row (+ one for threads 0..3), one running pointer.
+  // (Round 1 copied 4 bytes at a time from two separate images: 6 LDGSTS + their 64-bit addresses per thread and row,
+  // a fifth of the kernel's instructions.)  Chunks beyond the row are zero-filled (src-size 0); the pad column of an
+  // odd F holds whatever K1 left there: it only reaches outputs that ok0 / ok1 mask.
+  const bool in0 = (c0 + c) < Fp, in1 = t < 4 && (c0 + kSsimTC + c) < Fp;
+  const float2* g_next = img + (long long)r0 * Fp + c0 + (in0 ? c : 0);  // this thread's chunk of the row issued next
+  const int off1 = in1 ? kSsimTC : 0;
+  const unsigned sdst0 = (unsigned)__cvta_generic_to_shared(&rowbuf[0][c]);
+  const unsigned sdst1 = (unsigned)__cvta_generic_to_shared(&rowbuf[0][t < 4 ? kSsimTC + c : c]);
   int rows_left = r_end - r0;
   constexpr unsigned kStageBytes = RB * sizeof(float2);
   auto issue_row = [&](int stage) {
     if (rows_left > 0) {
       const unsigned sb = stage * kStageBytes;
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        if (u < 2 || t < 8) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst[u] + sb), "l"(e_next + coff[u]),
-                       "r"(cbytes[u])
-                       : "memory");
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst[u] + sb + 4u),
-                       "l"(g_next + coff[u]), "r"(cbytes[u])
-                       : "memory");
-        }
-      }
-      e_next += F;
-      g_next += F;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst0 + sb), "l"(g_next), "r"(in0 ? 16 : 0)
+                   : "memory");
+      if (t < 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst1 + sb), "l"(g_next + off1),
+                     "r"(in1 ? 16 : 0)
+                     : "memory");
+      g_next += Fp;
       --rows_left;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -161,7 +156,8 @@ k_ssim(const float* __restrict__ spec_e, const float* __restrict__ spec_t,
             const float vxy = cov_norm * (uxy - u1.x * u1.y);
             const float A1 = 2.f * u1.x * u1.y + C1, A2 = 2.f * vxy + C2;
             const float B1 = u1.x * u1.x + u1.y * u1.y + C1, B2 = var.x + var.y + C2;
-            const float S = __fdividef(A1 * A2, B1 * B2);
+            // B1 * B2 >= C1 * C2 = 1.44e-6: no denormal-range rescue needed, the bare MUFU.RCP (<= 1 ulp) + one multiply
+            const float S = (A1 * A2) * rcp_approx(B1 * B2);
             if (o == 0 ? ok0 : ok1) acc += S;
           }
         }

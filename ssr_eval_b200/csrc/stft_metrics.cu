@@ -121,11 +121,11 @@ static int plan_layout(const ssr_stft_plan* plan, const int64_t* offs, int n, un
   o = align_up(o + sizeof(double) * kPartials * (size_t)n_items, 256);
   w->ssim_part = o;
   if (flags & SSR_METRIC_SSIM) o = align_up(o + sizeof(double) * (size_t)n * w->tiles_per_pair, 256);
+  // K1 -> K2 spectrograms: one interleaved image of (estimate, target) pairs, even row pitch (k1_common.cuh: SpecLayout)
   w->spec_e = o;
-  if (flags & SSR_METRIC_SSIM) o = align_up(o + sizeof(float) * (size_t)total_frames * plan->F, 256);
-  w->spec_t = o;
+  w->spec_t = o + sizeof(float);
   if (flags & SSR_METRIC_SSIM)
-    o = align_up(o + sizeof(float) * (size_t)total_frames * plan->F, 256);
+    o = align_up(o + sizeof(float2) * (size_t)total_frames * spec_pitch_pairs(plan->F), 256);
   w->total = o;
   return SSR_OK;
 }
@@ -192,8 +192,9 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   int* item_pair = reinterpret_cast<int*>(ws + w.item_pair);
   long long* spec_off = reinterpret_cast<long long*>(ws + w.spec_off);
   double* partials = reinterpret_cast<double*>(ws + w.partials);
-  k_setup<<<1, 1024, 0, st>>>(offs_dev, n, plan->n_fft, plan->hop, w.chunk, plan->F, item_start,
-                              item_pair, spec_off);
+  const bool interleaved = spec_e && spec_t == spec_e + 1;
+  k_setup<<<1, 1024, 0, st>>>(offs_dev, n, plan->n_fft, plan->hop, w.chunk,
+                              interleaved ? 2 * spec_pitch_pairs(plan->F) : plan->F, item_start, item_pair, spec_off);
   SSR_LAUNCH_CHECK("k_setup");
   size_t smem = sizeof(cd) * (size_t)padded_size(plan->M);
   const int sms = sm_count();
@@ -525,9 +526,9 @@ static int metrics_batched_impl(const ssr_stft_plan* plan, const float* est_dev,
     for (int p0 = 0; p0 < n_pairs; p0 += 32768) {
       int np = n_pairs - p0 < 32768 ? n_pairs - p0 : 32768;
       dim3 grid(w.tiles_per_pair, np);
-      k_ssim<<<grid, kSsimThreads, 0, st>>>(spec_e, spec_t, reinterpret_cast<long long*>(ws + w.spec_off),
-                                       offs, p0, plan->n_fft, plan->hop, plan->F, w.tiles_x,
-                                       w.tiles_per_pair, ssim_part);
+      k_ssim<<<grid, kSsimThreads, 0, st>>>(reinterpret_cast<const float2*>(spec_e),
+                                            reinterpret_cast<long long*>(ws + w.spec_off), offs, p0, plan->n_fft,
+                                            plan->hop, plan->F, w.tiles_x, w.tiles_per_pair, ssim_part);
       SSR_LAUNCH_CHECK("k_ssim");
     }
   }
