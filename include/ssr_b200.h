@@ -66,7 +66,8 @@ int ssr_stft_plan_destroy(ssr_stft_plan* plan);
 /* frames of a centred STFT of `length` samples: 1 + (length + 2*(n_fft/2) - n_fft) / hop */
 int64_t ssr_stft_num_frames(const ssr_stft_plan* plan, int64_t length);
 
-/* workspace bytes needed by ssr_stft_metrics_batched for this batch and flag set */
+/* workspace bytes needed by ssr_stft_metrics_batched for this batch and flag set; the workspace pointer must be
+ * 16-byte aligned (any cudaMalloc / torch allocation is) */
 size_t ssr_stft_metrics_workspace_bytes(const ssr_stft_plan* plan, const int64_t* offsets_host,
                                         int n_pairs, unsigned flags);
 

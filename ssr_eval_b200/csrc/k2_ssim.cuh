@@ -139,9 +139,11 @@ k_ssim(const float2* __restrict__ spec2, const long long* __restrict__ spec_off,
           const float2 H1 = add2(S1, pe);
           const float2 H2 = fma2(pe, pe, S2);
           const float hxy = fmaf(pe.x, pe.y, sxy);
-          V1[o] = add2(V1[o], sub2(H1, R1[s][o]));
-          V2[o] = add2(V2[o], sub2(H2, R2[s][o]));
-          Vxy[o] += hxy - Rxy[s][o];
+          // (V - oldest) + newest: the oldest row's sums are dead before the newest are formed, so the ring slot is
+          // overwritten in place (V + (newest - oldest) cost 10 register moves per row)
+          V1[o] = add2(sub2(V1[o], R1[s][o]), H1);
+          V2[o] = add2(sub2(V2[o], R2[s][o]), H2);
+          Vxy[o] = (Vxy[o] - Rxy[s][o]) + hxy;
           R1[s][o] = H1;
           R2[s][o] = H2;
           Rxy[s][o] = hxy;

@@ -513,6 +513,8 @@ static int metrics_batched_impl(const ssr_stft_plan* plan, const float* est_dev,
   if (rc != SSR_OK) return rc;
   if (!workspace_dev || workspace_bytes < w.total)
     return fail(SSR_ERR_WORKSPACE, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace_dev) & 15)  // K2 streams the spectrogram rows with 16-byte copies
+    return fail(SSR_ERR_INVALID, "ssr_stft_metrics_batched: the workspace must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned char* ws = static_cast<unsigned char*>(workspace_dev);
   const long long* offs = reinterpret_cast<const long long*>(offsets_dev);
