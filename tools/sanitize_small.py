@@ -34,7 +34,7 @@ def main():
         for flags in ((N.METRIC_ALL,) if quick else (N.METRIC_LSD, 7, N.METRIC_ALL)):
             r = eng.metrics(est, tgt, flags)
         print("K1/K2 n_fft %d hop %d ok" % (n_fft, hop), r[0], flush=True)
-    for up, down in ([(160, 147)] if quick else [(160, 147), (441, 160), (80, 147), (3, 1)]):
+    for up, down in ([(160, 147), (147, 160)] if quick else [(160, 147), (147, 160), (441, 160), (147, 80), (80, 147), (3, 1)]):
         y = PolyphaseResampler(up, down).resample(tgt)
         print("K3 %d/%d ok" % (up, down), len(y[0]), flush=True)
     lp = HardLowpass(2048, 441)
