@@ -189,14 +189,23 @@ k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict
             v[q] = cd{tt * pcw[q].x - ee * pcw[q].y, tt * pcw[q].y + ee * pcw[q].x};
           }
         }
-        // the loads of the next sub-transform fly during all passes of this one
+#ifdef SSR_PFA_FETCH_EARLY
         if (r + 1 < R) fetch_inputs(f, r + 1);
         else if (fi + 1 < nf) fetch_inputs(f + 1, 0);
+#endif
         bfly16<false>(v);
         apply_tw1(v, std::false_type{});
         __syncthreads();  // previous sub-transform's last loads are done
 #pragma unroll
         for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
+#ifndef SSR_PFA_FETCH_EARLY
+        // The loads of the next sub-transform fly during the remaining five passes of this one.  Issued here, where
+        // v[] has just been stored and nothing else is live, not before pass 1: there the 36 prefetch registers met
+        // the butterfly and the tensor-memory twiddle buffers, ptxas spilled four of the just-loaded values and each
+        // spill store waited for its own load (ncu: 5.8 % of the warp time on STL / LDL)
+        if (r + 1 < R) fetch_inputs(f, r + 1);
+        else if (fi + 1 < nf) fetch_inputs(f + 1, 0);
+#endif
         __syncthreads();
         // ---- forward pass 2
 #pragma unroll
