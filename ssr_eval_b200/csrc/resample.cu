@@ -9,6 +9,10 @@
 //   y = upfirdn(h_padded, x, up, down)[n_pre_remove : n_pre_remove + n_out]   (zero extension)
 // i.e.  y[j] = sum_i x[i] * h[(j + n_pre_remove)*down - n_pre_pad - i*up], accumulated in float32
 // in ascending i with a separate multiply and add -- reproduced here term for term.
+//
+// Kernels: k_resample_pair (the evaluation's sample-rate pairs: TMA-staged span, two outputs
+// per thread over one LDS.64 window, table-driven prologue), k_resample_bulk (any K <= 48: TMA-staged span, one
+// output per thread-step), k_resample_tiled (index ranges beyond 32 bits), k_resample<T> (everything else, float64).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -43,9 +47,6 @@ struct ssr_resample_plan {
 
 namespace ssr {
 
-#ifndef SSR_K3_MINB320
-#define SSR_K3_MINB320 3
-#endif
 #ifndef SSR_K3_MIN_TP
 #define SSR_K3_MIN_TP 128  // smallest CTA of k_resample_pair (measured: 160 threads x 5 CTAs per SM beat 320 x 3)
 #endif
@@ -342,19 +343,6 @@ k_resample_pair(const float* __restrict__ x, const long long* __restrict__ in_of
   const bool st2 = (reinterpret_cast<uintptr_t>(yu) & 7) == 0;  // yu + ja is then 8-byte aligned (ja is even)
   if (bulk) mbar_wait(&bar, 0);
   else __syncthreads();
-#ifdef SSR_K3_LOOP_OLD
-#pragma unroll 2
-  for (int r = 0; r < RP; ++r) {
-    const float2* p = reinterpret_cast<const float2*>(xs_raw + A0 + r * step);
-    float accA = 0.f, accB = 0.f;
-#pragma unroll
-    for (int n = 0; n < NL; ++n) {
-      const float2 v = p[n];
-      const float2 pa = mul2(v, gA[n]), pb = mul2(v, gB[n]);
-      accA = __fadd_rn(__fadd_rn(accA, pa.x), pa.y);
-      accB = __fadd_rn(__fadd_rn(accB, pb.x), pb.y);
-    }
-#else
   const unsigned xs_addr = (unsigned)__cvta_generic_to_shared(xs_raw + A0);
 #pragma unroll 1
   for (int r = 0; r < RP; ++r) {
@@ -372,7 +360,6 @@ k_resample_pair(const float* __restrict__ x, const long long* __restrict__ in_of
       accA = __fadd_rn(__fadd_rn(accA, pa.x), pa.y);
       accB = __fadd_rn(__fadd_rn(accB, pb.x), pb.y);
     }
-#endif
     const unsigned j = ja + (unsigned)r * 2u * TP;
     if (j + 1 < n_out) {
       if (st2) *reinterpret_cast<float2*>(yu + j) = make_float2(accA, accB);
@@ -676,7 +663,7 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
   } while (0)
         // register caps: the largest that keep MINB CTAs of MAXT threads on an SM (64 / 72 / 80 registers)
         if (NL == 12 && TPP <= 160) SSR_K3P_LAUNCH(12, 160, 5);
-        else if (NL == 12 && TPP <= 320) SSR_K3P_LAUNCH(12, 320, SSR_K3_MINB320);  // 44.1k -> 48k (160/147)
+        else if (NL == 12 && TPP <= 320) SSR_K3P_LAUNCH(12, 320, 3);  // 44.1k -> 48k (160/147)
         else if (NL == 12) SSR_K3P_LAUNCH(12, 448, 2);                // 16k -> 44.1k (441/160), 8k / 12k / 24k -> 44.1k
         else if (TPP <= 160) SSR_K3P_LAUNCH(13, 160, 5);              // 48k -> 44.1k (147/160)
         else if (TPP <= 320) SSR_K3P_LAUNCH(13, 320, 2);              // 48k -> 44.1k (147/160)
