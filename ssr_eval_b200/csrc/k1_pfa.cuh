@@ -153,9 +153,12 @@ k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict
     double s_et = 0, s_tt = 0, s_ee = 0, l_et = 0, l_tt = 0, l_ee = 0;
 
     // inputs of sub-transform (f, r): samples of both signals and window*chirp, NQ per thread
+    // The samples (stride-R gathers) are held in registers from one sub-transform to the next; their window * chirp
+    // factors are only pulled towards L1 and loaded where they are used.  Measured (gpurun sessions s36 / s37): holding
+    // the factors in registers too (24 more, ptxas spills) 36.2 k pairs/s, this form 37.3 k, no register prefetch at
+    // all 32.6 k.
     float ptx[NQ];
     ET pex[NQ];
-    cd pcw[NQ];
     auto fetch_inputs = [&](long long f, int r) {
       const long long start = f * hop - N / 2;
       const bool interior = (start >= 0 && start + N <= L);
@@ -164,13 +167,12 @@ k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict
         const int n = tid + 128 * q;
         ptx[q] = 0.f;
         pex[q] = (ET)0;
-        pcw[q] = cd{0.0, 0.0};
         if (n < P) {
           const long long si = start + (long long)R * n + r;
           const long long idx = interior ? si : reflect_index(si, L);
           ptx[q] = __ldg(xt + idx);
           pex[q] = __ldg(xe + idx);
-          pcw[q] = D.cwin[r * P + n];
+          prefetch_l1(D.cwin + r * P + n);
         }
       }
     };
@@ -186,7 +188,9 @@ k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict
           v[q] = cd{0.0, 0.0};
           if (q < NQ) {
             const double tt = (double)ptx[q], ee = (double)pex[q];
-            v[q] = cd{tt * pcw[q].x - ee * pcw[q].y, tt * pcw[q].y + ee * pcw[q].x};
+            const int n = tid + 128 * q;
+            const cd cw = (n < P) ? D.cwin[r * P + n] : cd{0.0, 0.0};
+            v[q] = cd{tt * cw.x - ee * cw.y, tt * cw.y + ee * cw.x};
           }
         }
 #ifdef SSR_PFA_FETCH_EARLY
@@ -200,7 +204,7 @@ k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict
         for (int q = 0; q < 16; ++q) b1[144 * q] = v[q];
 #ifndef SSR_PFA_FETCH_EARLY
         // The loads of the next sub-transform fly during the remaining five passes of this one.  Issued here, where
-        // v[] has just been stored and nothing else is live, not before pass 1: there the 36 prefetch registers met
+        // v[] has just been stored and nothing else is live, not before pass 1: there the prefetch registers met
         // the butterfly and the tensor-memory twiddle buffers, ptxas spilled four of the just-loaded values and each
         // spill store waited for its own load (ncu: 5.8 % of the warp time on STL / LDL)
         if (r + 1 < R) fetch_inputs(f, r + 1);
