@@ -536,6 +536,27 @@ def test_repeatable_under_workspace_poisoning(engines, n_fft, hop):
         assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(ref, nan=-1.0)), poison
 
 
+def test_metrics_reject_a_misaligned_workspace(engines):
+    """K2 streams the interleaved K1 -> K2 image with 16-byte copies: a workspace pointer that is not 16-byte aligned
+    must be refused by the C ABI (include/ssr_b200.h), not produce a misaligned-address fault."""
+    from ssr_eval_b200 import engine as E
+    eng = engines(2048, 512)
+    t = torch.from_numpy(speech_like(30000, sr=48000, seed=5)).cuda()
+    e = (0.5 * t).contiguous()
+    off = np.array([0, 30000], dtype=np.int64)
+    off_d = torch.from_numpy(off).cuda()
+    out = torch.empty(4, dtype=torch.float64, device="cuda")
+    need = N.lib().ssr_stft_metrics_workspace_bytes(eng._plan, E._np_ptr(off), 1, N.METRIC_ALL)
+    ws = torch.empty(need + 64, dtype=torch.uint8, device="cuda")
+    args = (eng._plan, E._ptr(e), E._ptr(t), E._np_ptr(off), E._ptr(off_d), 1, N.METRIC_ALL, E._ptr(out))
+    rc = N.lib().ssr_stft_metrics_batched(*args, E._ptr(ws) + 4, need, E._stream())
+    assert rc != 0 and b"16-byte aligned" in N.lib().ssr_last_error()
+    rc = N.lib().ssr_stft_metrics_batched(*args, E._ptr(ws) + 16, need, E._stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.isfinite(out.cpu().numpy()).all()
+
+
 def _helper_reference_runs():
     import json
     import os
