@@ -7,7 +7,7 @@ OBJ := build/obj
 LIB := ssr_eval_b200/lib/libssr_b200.so
 SRCS := $(SRC)/stft_metrics.cu $(SRC)/resample.cu $(SRC)/stft_lowpass.cu $(SRC)/stft_splice.cu $(SRC)/sosfiltfilt.cu $(SRC)/pcm.cu $(SRC)/stft_lowpass_dense.cu $(SRC)/xcorr_align.cu
 OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(SRCS))
-HDRS := $(wildcard $(SRC)/*.cuh) $(SRC)/stft_tables.hpp include/ssr_b200.h Makefile
+HDRS := $(wildcard $(SRC)/*.cuh) $(SRC)/stft_tables.hpp $(SRC)/resample_tables.hpp include/ssr_b200.h Makefile
 
 all: $(LIB)
 
@@ -20,7 +20,7 @@ $(LIB): $(OBJS)
 	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -cudart static
 
 # host-side emulation harness for the FFT core (no GPU needed)
-build/host_emul: tests/host_emul.cu $(SRC)/fft_core.cuh $(SRC)/stft_tables.hpp $(SRC)/k1_map.cuh
+build/host_emul: tests/host_emul.cu $(SRC)/fft_core.cuh $(SRC)/stft_tables.hpp $(SRC)/k1_map.cuh $(SRC)/resample_tables.hpp
 	@mkdir -p build
 	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -o $@ $<
 

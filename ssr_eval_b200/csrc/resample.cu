@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "f32x2.cuh"
+#include "resample_tables.hpp"
 
 struct ssr_resample_plan {
   int up, down, n_taps, half_len, n_pre_pad, n_pre_remove, K, device;
@@ -47,13 +48,6 @@ struct ssr_resample_plan {
 
 namespace ssr {
 
-#ifndef SSR_K3_MIN_TP
-#define SSR_K3_MIN_TP 128  // smallest CTA of k_resample_pair (measured: 160 threads x 5 CTAs per SM beat 320 x 3)
-#endif
-#ifndef SSR_K3_RP
-#define SSR_K3_RP 16  // output pairs per thread of k_resample_pair
-#endif
-constexpr int kBankStride = 512;  // row stride of the transposed banks (floats / float2s): up <= 512
 
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
@@ -419,53 +413,21 @@ static cudaError_t make_staged_banks(ssr_resample_plan* p, const float* bank_hos
   p->pair_g = nullptr;
   p->pair_thr = nullptr;
   p->pair_nl = p->pair_tp = p->pair_m = 0;
-  const int up = p->up, down = p->down, K = p->K;
-  if (up > kBankStride) return cudaSuccess;  // the staged kernels are not used for such plans
-  std::vector<int> phase(up);
-  for (int n = 0; n < up; ++n) phase[n] = (int)(((long long)p->half_len + (long long)n * down) % up);
-  std::vector<float> t((size_t)K * kBankStride, 0.f);
-  for (int k = 0; k < K; ++k)
-    for (int n = 0; n < up; ++n) t[(size_t)k * kBankStride + n] = bank_host[(size_t)phase[n] * K + k];
-  cudaError_t e = upload(&p->bank_t, t);
+  if (p->up > kBankStride) return cudaSuccess;  // the staged kernels are not used for such plans
+  // table construction: resample_tables.hpp (shared with the CPU emulation of k_resample_pair, tests/host_emul.cu)
+  cudaError_t e = upload(&p->bank_t, k3_build_bank_t(p->up, p->down, p->K, p->half_len, bank_host));
   if (e != cudaSuccess) return e;
-  // k_resample_pair: instantiated for windows of 24 / 26 words (K = 21 / 22 of the evaluation's sample-rate pairs);
-  // block: 2 * TP = m * up outputs with m * down even (the window alignment repeats), smallest TP >= SSR_K3_MIN_TP
-  const int d_max = (down + up - 1) / up;
-  const int NL = (K + d_max + 1 + 1) / 2;
-  if (NL != 12 && NL != 13) return cudaSuccess;
-  int m = 0;
-  for (int c = 1; (long long)c * up <= 1024; ++c)
-    if (((long long)c * up) % 2 == 0 && ((long long)c * down) % 2 == 0 && c * up / 2 >= SSR_K3_MIN_TP) {
-      m = c;
-      break;
-    }
-  if (m == 0) return cudaSuccess;
-  const int TP = m * up / 2;
-  auto tap = [&](int ph, int k) { return (k >= 0 && k < K) ? bank_host[(size_t)ph * K + k] : 0.f; };
-  std::vector<float2> g((size_t)2 * 2 * NL * kBankStride, make_float2(0.f, 0.f));
-  const int P = (up % 2 == 0) ? up / 2 : up;  // distinct output pairs (mod up) a CTA's threads see
-  for (int par = 0; par < 2; ++par)
-    for (int c = 0; c < P; ++c) {
-      const int n = (2 * c) % up;
-      const int pa = phase[n], pb = phase[(n + 1) % up];
-      const int ka0 = K - 1 + par, kb0 = ka0 + (pa + down) / up;
-      for (int q = 0; q < NL; ++q) {
-        g[((size_t)par * 2 * NL + q) * kBankStride + c] = make_float2(tap(pa, ka0 - 2 * q), tap(pa, ka0 - 2 * q - 1));
-        g[((size_t)par * 2 * NL + NL + q) * kBankStride + c] =
-            make_float2(tap(pb, kb0 - 2 * q), tap(pb, kb0 - 2 * q - 1));
-      }
-    }
-  std::vector<int2> thr(TP);
-  for (int th = 0; th < TP; ++th) {
-    const long long c = (long long)p->half_len + 2LL * th * down;
-    thr[th] = make_int2((int)(c / up - p->half_len / up), th % P);
-  }
-  e = upload(&p->pair_g, g);
-  if (e == cudaSuccess) e = upload(&p->pair_thr, thr);
+  K3PairTables pt;
+  if (!k3_build_pair_tables(p->up, p->down, p->K, p->half_len, bank_host, &pt)) return cudaSuccess;
+  static_assert(sizeof(float2) == 2 * sizeof(float) && sizeof(int2) == 2 * sizeof(int), "flattened pair layouts");
+  e = cudaMalloc(&p->pair_g, pt.g.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(p->pair_g, pt.g.data(), pt.g.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&p->pair_thr, pt.thr.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(p->pair_thr, pt.thr.data(), pt.thr.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
-  p->pair_nl = NL;
-  p->pair_tp = TP;
-  p->pair_m = m;
+  p->pair_nl = pt.nl;
+  p->pair_tp = pt.tp;
+  p->pair_m = pt.m;
   return cudaSuccess;
 }
 
@@ -634,12 +596,10 @@ int ssr_resample_poly_batched(const ssr_resample_plan* plan, const float* x_dev,
     // production path for the sample-rate pairs of the evaluation (K = 21 / 22): two consecutive outputs per thread
     // (block size and tables: make_staged_banks)
     constexpr int RP = SSR_K3_RP;
-    const int d_max = (plan->down + plan->up - 1) / plan->up;
     const int NL = plan->pair_nl;  // 64-bit loads covering K + d_max samples at either alignment
     const int TPP = plan->pair_tp;
     const long long outs = 2LL * TPP * RP;
-    // samples the CTA's windows reach: newest(last) - newest(first) + K, + d_max, + the zero-tap overhang of a window
-    const long long spanp = (outs - 1) * plan->down / plan->up + 2 + plan->K + d_max + 2 * NL - plan->K + 2;
+    const long long spanp = k3_pair_span(plan->up, plan->down, plan->K, NL, TPP, RP);
     const long long c_max = (max_out + outs) * plan->down + plan->half_len;
     if (NL > 0 && plan->pair_g && plan->pair_thr && (spanp + 8) * (long long)sizeof(float) <= 64 * 1024 &&
         c_max < 0x7fffffffLL && max_in < 0x7fffffffLL && !force_old_k3() && !force_bulk_k3()) {

@@ -4,9 +4,11 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
+#include "../ssr_eval_b200/csrc/resample_tables.hpp"
 #include "../ssr_eval_b200/csrc/stft_tables.hpp"
 #include "../ssr_eval_b200/csrc/k1_map.cuh"
 
@@ -313,8 +315,106 @@ static int check_pfa(int n_fft) {
   return (errT < 1e-11 * (1 + magT) && errE < 1e-11 * (1 + magT)) ? 0 : 1;
 }
 
+// K3 k_resample_pair, emulated thread by thread exactly as the kernel indexes (resample.cu): staged span (bulk copy from
+// the 16-byte-aligned address below it, or element-wise with zero extension at the ends), even-aligned LDS.64 window,
+// shifted zero-padded filter pairs from the plan's tables, additions oldest sample first.  Must reproduce the plain
+// polyphase sum y[j] = sum_k x[i(j) - k] * bank[phase(j)][k] (float32 multiply, then add; k = K-1 .. 0) BIT FOR BIT,
+// and may never read a shared-memory word that was not staged.
+static int check_k3_pair(int up, int down, int n_in, int buffer_shift) {
+  const int half_len = 10 * (up > down ? up : down), n_taps = 2 * half_len + 1, K = (n_taps + up - 1) / up;
+  std::vector<float> taps(n_taps);
+  for (int i = 0; i < n_taps; ++i) {  // any odd-length filter will do: windowed sinc with an irrational-ish scale
+    const double t = (i - half_len) / (double)(up > down ? up : down), w = 0.54 + 0.46 * cos((double)kPiL * (i - half_len) / half_len);
+    taps[i] = (float)(w * (t == 0 ? 1.0 : sin((double)kPiL * t) / ((double)kPiL * t)) * (double)up / (up > down ? up : down) * 0.97);
+  }
+  std::vector<float> bank((size_t)up * K, 0.f);
+  for (int ph = 0; ph < up; ++ph)
+    for (int k = 0; k < K; ++k) {
+      const long long q = ph + (long long)k * up;
+      if (q < n_taps) bank[(size_t)ph * K + k] = taps[q];
+    }
+  K3PairTables pt;
+  if (!k3_build_pair_tables(up, down, K, half_len, bank.data(), &pt)) { printf("k3 pair %d/%d: no tables\n", up, down); return 1; }
+  const int NL = pt.nl, TP = pt.tp, RP = SSR_K3_RP;
+  const int span = (int)k3_pair_span(up, down, K, NL, TP, RP);
+  const int step = pt.m * down;
+  if (step % 2 != 0 || (2 * TP) % up != 0) { printf("k3 pair %d/%d: bad block %d\n", up, down, TP); return 1; }
+  std::vector<float> x(n_in);
+  for (int i = 0; i < n_in; ++i) x[i] = (float)frand();
+  const long long n_out = ((long long)n_in * up + down - 1) / down;
+  std::vector<float> want(n_out), got(n_out, nanf(""));
+  for (long long j = 0; j < n_out; ++j) {
+    const long long c = j * down + half_len, i = c / up;
+    const int ph = (int)(c % up);
+    float acc = 0.f;
+    for (int k = K - 1; k >= 0; --k) {
+      const long long s = i - k;
+      const float xv = (s >= 0 && s < n_in) ? x[s] : 0.f;
+      const volatile float prod = xv * bank[(size_t)ph * K + k];  // separate rounding of the product (no contraction)
+      acc = acc + prod;
+    }
+    want[j] = acc;
+  }
+  const long long outs = 2LL * TP * RP, xoff = buffer_shift;  // xoff: where the utterance starts inside the batch buffer
+  const unsigned ib0 = half_len / up, ib_step = (unsigned)(pt.m * RP * down);
+  int unstaged = 0;
+  for (long long blk = 0; blk * outs < n_out; ++blk) {
+    const long long jb = blk * outs;
+    const long long ib = ib0 + blk * ib_step;
+    if (ib != (jb * down + half_len) / up) { printf("k3 pair: ib mismatch\n"); return 1; }
+    const long long i_base = ib - (K - 1), g0 = xoff + i_base;
+    const int shift = (int)(g0 & 3), n_copy = (span + shift + 3) & ~3;
+    const bool bulk = i_base >= 0 && i_base + span <= n_in;  // (the batch-buffer end test needs a second utterance)
+    const int sh = bulk ? shift : 0;
+    std::vector<float> xs(span + 8, nanf(""));
+    if (bulk) {
+      for (int i = 0; i < n_copy; ++i) {
+        const long long gi = i_base - shift + i;
+        xs[i] = (gi >= 0 && gi < n_in) ? x[gi] : 123.0f;  // a neighbouring utterance's sample: finite, times a zero tap
+      }
+    } else {
+      for (int i = 0; i < span; ++i) {
+        const long long gi = i_base + i;
+        xs[i] = (gi >= 0 && gi < n_in) ? x[gi] : 0.f;
+      }
+    }
+    for (int t = 0; t < TP; ++t) {
+      const long long ja = jb + 2 * t;
+      const int rel = pt.thr[2 * t], col = pt.thr[2 * t + 1];
+      const int a_lo = rel + sh, A0 = a_lo & ~1, par = a_lo & 1;
+      for (int r = 0; r < RP; ++r) {
+        const long long j = ja + (long long)r * 2 * TP;
+        if (j >= n_out) continue;
+        float accA = 0.f, accB = 0.f;
+        for (int n = 0; n < NL; ++n) {
+          const float v0 = xs[A0 + r * step + 2 * n], v1 = xs[A0 + r * step + 2 * n + 1];
+          if (v0 != v0 || v1 != v1) ++unstaged;
+          const float* ga = &pt.g[2 * (((size_t)par * 2 * NL + n) * kBankStride + col)];
+          const float* gb = &pt.g[2 * (((size_t)par * 2 * NL + NL + n) * kBankStride + col)];
+          const volatile float a0 = v0 * ga[0], a1 = v1 * ga[1], b0 = v0 * gb[0], b1 = v1 * gb[1];
+          accA = (accA + a0) + a1;
+          accB = (accB + b0) + b1;
+        }
+        got[j] = accA;
+        if (j + 1 < n_out) got[j + 1] = accB;
+      }
+    }
+  }
+  long long diff = 0;
+  for (long long j = 0; j < n_out; ++j) diff += memcmp(&want[j], &got[j], sizeof(float)) != 0 && !(want[j] == 0.f && got[j] == 0.f);
+  printf("k3 pair %3d/%3d n_in %6d buffer shift %d: TP %3d NL %d, %lld outputs, %lld differ, %d unstaged reads\n", up, down,
+         n_in, buffer_shift, TP, NL, n_out, diff, unstaged);
+  return (diff == 0 && unstaged == 0) ? 0 : 1;
+}
+
 int main() {
   int bad = 0;
+  {
+    const int ratios[5][2] = {{160, 147}, {147, 160}, {441, 160}, {441, 80}, {147, 80}};
+    const int lens[4] = {30011, 52345, 17001, 40000};
+    for (int i = 0; i < 5; ++i)
+      for (int s = 0; s < 4; ++s) bad += check_k3_pair(ratios[i][0], ratios[i][1], lens[s], s);
+  }
   bad += check_pfa(2229);
   bad += check_pfa(1114);
   bad += check_pfa(743);

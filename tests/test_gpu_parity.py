@@ -549,9 +549,10 @@ def test_metrics_reject_a_misaligned_workspace(engines):
     need = N.lib().ssr_stft_metrics_workspace_bytes(eng._plan, E._np_ptr(off), 1, N.METRIC_ALL)
     ws = torch.empty(need + 64, dtype=torch.uint8, device="cuda")
     args = (eng._plan, E._ptr(e), E._ptr(t), E._np_ptr(off), E._ptr(off_d), 1, N.METRIC_ALL, E._ptr(out))
-    rc = N.lib().ssr_stft_metrics_batched(*args, E._ptr(ws) + 4, need, E._stream())
+    import ctypes
+    rc = N.lib().ssr_stft_metrics_batched(*args, ctypes.c_void_p(ws.data_ptr() + 4), need, E._stream())
     assert rc != 0 and b"16-byte aligned" in N.lib().ssr_last_error()
-    rc = N.lib().ssr_stft_metrics_batched(*args, E._ptr(ws) + 16, need, E._stream())
+    rc = N.lib().ssr_stft_metrics_batched(*args, ctypes.c_void_p(ws.data_ptr() + 16), need, E._stream())
     assert rc == 0
     torch.cuda.synchronize()
     assert np.isfinite(out.cpu().numpy()).all()
