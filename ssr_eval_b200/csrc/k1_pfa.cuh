@@ -26,7 +26,11 @@ namespace ssr {
 // float64 from the waveform to the sums -- np.abs(complex128), float64 log10 / products -- only T is rounded to
 // complex64 / float32; same arithmetic as the generic kernel's float64-estimate path, 4x its speed.
 template <int NQ, int FIXED, typename ET = float>
-__global__ void __launch_bounds__(kV2Threads, 3)
+#ifndef SSR_PFA_CTAS
+#define SSR_PFA_CTAS 3  // CTAs per SM of the PFA kernels (168 registers; 2 CTAs with the ~220 registers ptxas then
+                        // takes and no spill: 32.2 k pairs/s against 37.3 k -- the warps matter more)
+#endif
+__global__ void __launch_bounds__(kV2Threads, SSR_PFA_CTAS)
 k_stft_metrics_pfa(PfaDev D, const ET* __restrict__ est, const float* __restrict__ tgt,
                    const long long* __restrict__ offsets, const int* __restrict__ item_start,
                    const int* __restrict__ item_pair, int n_items, int chunk, unsigned flags,

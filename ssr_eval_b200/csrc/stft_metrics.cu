@@ -214,7 +214,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
     // float64 estimate on the PFA kernel (n_fft = R * P, e.g. 2229 at 48 kHz): same arithmetic as the generic kernel's
     // float64-estimate path at ~4x its speed -- the IIR low-pass keys of setting_lowpass_filtering all come this way
     const size_t smem_p = sizeof(cd) * (2048 + 256) + sizeof(cd) * (size_t)(plan->n_fft - plan->pdev.P);
-    int gp = sms * 3;
+    int gp = sms * SSR_PFA_CTAS;
     if (gp > w.n_items) gp = w.n_items;
     const int nq = (plan->pdev.P + 127) / 128;
 #define SSR_PFA64_LAUNCH(NQ_)                                                                        \
@@ -258,7 +258,7 @@ static int run_k1(const ssr_stft_plan* plan, const WsLayout& w, cudaStream_t st,
   }
   if (plan->pfa && !force_generic_k1()) {
     const size_t smem_p = sizeof(cd) * (2048 + 256) + sizeof(cd) * (size_t)(plan->n_fft - plan->pdev.P);
-    int gp = sms * 3;
+    int gp = sms * SSR_PFA_CTAS;
     if (gp > w.n_items) gp = w.n_items;
     const bool store = spec_e || spec_t;
     const bool lsd_only = !store && (flags & 7u) == 1u;
