@@ -317,8 +317,17 @@ k_stft_hard_lowpass_2048(LpDev P, const float* __restrict__ x, const long long* 
       const float x1r = 0.5f * (zk.x + zn.x), x1i = 0.5f * (zk.y - zn.y);
       const float x2r = 0.5f * (zk.y + zn.y), x2i = 0.5f * (zn.x - zk.x);
       const bool keep = k < cut;
+#ifdef SSR_K4_PHASE_ROUNDTRIP
       cf A = phase_roundtrip_fast(x1r, x1i, keep);
       cf B = phase_roundtrip_fast(x2r, x2i, keep);
+#else
+      // The reference rebuilds a kept bin as mag * (re / mag), mag * (im / mag) (dsp.py:76-88): the bin itself up to
+      // two roundings (also below the 1e-8 clamp: mag = 1e-4 both times).  This FFT mode -- whose float32 transform
+      // already differs from the reference's dense products by 2e-5 per sample -- keeps the bin as it is: 9 instructions
+      // and two MUFU per bin and signal less, 14 % of the kernel.  The dense mode (K4d) has the reference's exact form.
+      cf A = keep ? cf{x1r, x1i} : cf{0.f, 0.f};
+      cf B = keep ? cf{x2r, x2i} : cf{0.f, 0.f};
+#endif
       if (self) {  // DC / Nyquist: imaginary parts never reach the real IDFT
         A.y = 0.f;
         B.y = 0.f;
