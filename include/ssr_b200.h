@@ -147,8 +147,9 @@ int ssr_resample_plan_create_bank(ssr_resample_plan** plan, int up, int down, co
 /* ------------------------------------------------------------------------------------------
  * K4: STFT hard low-pass = stft_hard_lowpass_v0 (ssr_eval/lowpass.py:17-28) through
  * FDomainHelper.wav_to_spectrogram_phase / spectrogram_phase_to_wav (ssr_eval/dsp.py:76-119):
- * STFT (n_fft, hop, periodic Hann, centre, reflect) -> mag/cos/sin with eps 1e-8 -> zero bins
- * >= cut_bin -> ISTFT (x window / n_fft, overlap-add, / clamp(overlap-added window^2, 1e-11))
+ * STFT (n_fft, hop, periodic Hann, centre, reflect) -> zero bins >= cut_bin (kept bins pass through; the reference
+ * rebuilds them as mag*cos, mag*sin with eps 1e-8: the bin itself up to two roundings -- the dense mode below and the
+ * n_fft != 2048 kernel do that) -> ISTFT (x window / n_fft, overlap-add, / clamp(overlap-added window^2, 1e-11))
  * -> drop n_fft/2 -> exactly `length` samples.  float32 arithmetic.  n_fft must be a power of
  * two in [256, 4096]; the reference always uses n_fft 2048 / hop 441 (dsp.py:9-10).
  * cut_bins_dev: one int32 per utterance = int((n_fft/2+1) * lowpass_ratio).

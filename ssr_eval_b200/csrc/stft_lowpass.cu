@@ -7,7 +7,7 @@
 //   ssr_eval/dsp.py:107-119     spectrogram_phase_to_wav -> torchlibrosa ISTFT
 // torchlibrosa computes the STFT/ISTFT as dense conv1d DFTs in float32; here each CTA runs a
 // shared-memory float32 FFT instead, two real frames packed per complex transform:
-//   z = w*x_f + i*w*x_{f+1} -> FFT -> split -> mag/cos/sin round trip, zero k >= cut
+//   z = w*x_f + i*w*x_{f+1} -> FFT -> split -> zero k >= cut (generic kernel: + the mag/cos/sin round trip)
 //   -> Y = X'_f + i*X'_{f+1} (Hermitian extended) -> inverse FFT -> Re = frame f, Im = frame f+1
 //   -> x window / n_fft -> overlap-add in shared memory -> / clamp(sum window^2, 1e-11) -> trim.
 // A work item owns `chunk_hops` hops of output samples and recomputes the <= n_fft/hop halo frames.
@@ -155,7 +155,7 @@ k_stft_hard_lowpass(LpDev P, const float* __restrict__ x, const long long* __res
 // Specialised n_fft = 2048 kernel (the only size the reference uses, dsp.py:9): 128 threads, radix
 // 16 x 16 x 8 forward DIF and 8 x 16 x 16 inverse DIT in float32.  As in K1 every thread owns a last-
 // pass butterfly AND its Hermitian partner (k1_map.cuh), so the split of the two packed frames, the
-// mag/cos/sin round trip, the zeroing and the re-packing all happen in registers between the forward
+// zeroing and the re-packing all happen in registers between the forward
 // pass 3 and the inverse pass 1 -- 4 shared-memory exchanges per frame PAIR instead of 8.
 // float2 slots are padded as i + i/16 (conflict-free for the 8-byte accesses of all three passes).
 // ---------------------------------------------------------------------------------------------
